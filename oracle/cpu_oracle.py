@@ -1,0 +1,344 @@
+"""ORACLE -- test infrastructure, NOT product code.
+
+Python face of the CPU restatement (``qampy_oracle.c``) with the reference's own call
+signatures, plus a NumPy restatement of the thin L2 drivers that sit between the public
+API and the kernels.  Reference lines followed (paths relative to /root/reference/qampy):
+
+* L1 kernels: ``core/equalisation/pythran_equalisation.py:37-76, 130-173``,
+  ``core/pythran_dsp.py:47-85, 137-153`` (in C, see ``qo_kernels.inc``)
+* L2 drivers: ``core/equalisation/equalisation.py:101-136, 138-188, 271-281, 311-373,
+  400-466, 468-594`` and ``core/phaserecovery.py:141-159``
+* constellations: ``theory.py:111-178``
+
+Parity pin: ``tests/test_oracle_golden.py`` checks every function here against vectors
+produced by executing the reference's Python sources on the same inputs
+(``tests/golden/make_golden.py``).  The reference has no golden vectors of its own for
+this path (its tests are statistical).
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU legs may import this module.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import build as _build  # noqa: E402
+
+METHODS = {"cma": 0, "cma2": 1, "sgncma": 2, "mcma": 3, "rde": 4, "mrde": 5, "sbd": 6,
+           "sbd_data": 7, "mddma": 8, "dd": 9}
+NONDECISION_BASED = ("cma", "cma2", "mcma", "rde", "mrde", "sgncma")
+DATA_AIDED = ("sbd_data",)
+
+_libs = {}
+_c_long = ctypes.c_long
+_c_vp = ctypes.c_void_p
+
+
+def _declare(lib):
+    for suf, real in (("_f32", ctypes.c_float), ("_f64", ctypes.c_double)):
+        f = getattr(lib, "qo_train_equaliser" + suf)
+        f.restype = ctypes.c_int
+        f.argtypes = [_c_vp, _c_long, _c_long, _c_long, _c_long, _c_long, _c_long, _c_long, real,
+                      _c_vp, _c_long, _c_vp, _c_long, ctypes.c_int, _c_vp, _c_long, ctypes.c_int,
+                      ctypes.c_int, _c_vp, _c_vp]
+        f = getattr(lib, "qo_apply_filter_to_signal" + suf)
+        f.restype = ctypes.c_int
+        f.argtypes = [_c_vp, _c_long, _c_long, _c_long, _c_long, _c_long, _c_long, _c_vp, _c_long,
+                      _c_vp, _c_long, _c_vp]
+        f = getattr(lib, "qo_bps" + suf)
+        f.restype = ctypes.c_int
+        f.argtypes = [_c_vp, _c_long, _c_long, _c_long, _c_vp, _c_long, _c_long, _c_vp, _c_long,
+                      _c_long, _c_vp]
+        f = getattr(lib, "qo_select_angles" + suf)
+        f.restype = ctypes.c_int
+        f.argtypes = [_c_vp, _c_long, _c_long, _c_vp, _c_long, _c_vp]
+    lib.qo_max_threads.restype = ctypes.c_int
+    lib.qo_set_threads.argtypes = [ctypes.c_int]
+    return lib
+
+
+def lib(kind="strict"):
+    """kind: 'strict' (parity oracle), 'fast' (portable timed build), 'fast_native'."""
+    if kind not in _libs:
+        if kind == "strict":
+            path = _build.build_strict()
+        else:
+            path = _build.build_fast(native=(kind == "fast_native"))
+        _libs[kind] = _declare(ctypes.CDLL(path))
+    return _libs[kind]
+
+
+def _suf(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.complex64 or dtype == np.float32:
+        return "_f32", np.float32, np.complex64
+    if dtype == np.complex128 or dtype == np.float64:
+        return "_f64", np.float64, np.complex128
+    raise TypeError("oracle supports complex64/complex128 only, got %s" % dtype)
+
+
+def _p(a):
+    return a.ctypes.data_as(_c_vp)
+
+
+# --------------------------------------------------------------------------------------
+# L1: same signatures as the reference's Pythran exports
+# --------------------------------------------------------------------------------------
+def train_segments(E, TrSyms, Niter, os_, mu, wx, modes, adaptive, symbols, method,
+                   mu_shared=True, kind="strict"):
+    """Batched trainer: E (nseg, nmodes, L), wx (nseg, nmodes, nmodes, ntaps) updated in place.
+    Returns err (nseg, nmodes, TrSyms*Niter), wx, mu (nseg,)."""
+    if method not in METHODS:
+        raise ValueError("Unknown method %s" % method)
+    suf, rt, ct = _suf(E.dtype)
+    E = np.ascontiguousarray(E, dtype=ct)
+    assert E.ndim == 3 and wx.ndim == 4 and wx.dtype == ct and wx.flags.c_contiguous
+    nseg, nmodes, L = E.shape
+    ntaps = wx.shape[-1]
+    symbols = np.ascontiguousarray(symbols, dtype=ct)
+    assert symbols.ndim == 2 and symbols.shape[0] == nmodes
+    modes = np.ascontiguousarray(np.atleast_1d(modes), dtype=np.int64)
+    assert modes.max() < nmodes
+    if method == "sbd_data":
+        assert symbols.shape[1] >= TrSyms
+    assert (TrSyms - 1) * os_ + ntaps <= L, "training would read past the end of the signal"
+    err = np.zeros((nseg, nmodes, TrSyms * Niter), dtype=ct)
+    mu_out = np.full(nseg, mu, dtype=rt)
+    rc = getattr(lib(kind), "qo_train_equaliser" + suf)(
+        _p(E), nseg, nmodes * L, L, nmodes, TrSyms, Niter, os_, rt(mu), _p(wx), ntaps, _p(modes),
+        modes.size, int(bool(adaptive)), _p(symbols), symbols.shape[1], METHODS[method],
+        int(bool(mu_shared)), _p(err), _p(mu_out))
+    if rc:
+        raise RuntimeError("oracle train_equaliser failed rc=%d" % rc)
+    return err, wx, mu_out
+
+
+def train_equaliser(E, TrSyms, Niter, os_, mu, wx, modes, adaptive, symbols, method,
+                    mu_shared=True, kind="strict"):
+    """pythran_equalisation.py:130-173.  wx is updated in place and returned."""
+    assert wx.flags.c_contiguous
+    err, _, mu_out = train_segments(E[None], TrSyms, Niter, os_, mu, wx[None], modes, adaptive,
+                                    symbols, method, mu_shared, kind)
+    return err[0], wx, mu_out[0]
+
+
+def apply_segments(E, os_, wx, modes=None, kind="strict"):
+    suf, rt, ct = _suf(E.dtype)
+    E = np.ascontiguousarray(E, dtype=ct)
+    wx = np.ascontiguousarray(wx, dtype=ct)
+    nseg, nmodes, L = E.shape
+    ntaps = wx.shape[-1]
+    if modes is None:
+        modes = np.arange(wx.shape[1])
+    modes = np.ascontiguousarray(np.atleast_1d(modes), dtype=np.int64)
+    N = max((L - ntaps + 1) // os_, 0)
+    out = np.zeros((nseg, modes.size, N), dtype=ct)
+    rc = getattr(lib(kind), "qo_apply_filter_to_signal" + suf)(
+        _p(E), nseg, nmodes * L, L, nmodes, L, os_, _p(wx), ntaps, _p(modes), modes.size, _p(out))
+    if rc:
+        raise RuntimeError("oracle apply_filter_to_signal failed rc=%d" % rc)
+    return out
+
+
+def apply_filter_to_signal(E, os_, wx, modes=None, kind="strict"):
+    """pythran_equalisation.py:37-76."""
+    return apply_segments(E[None], os_, np.asarray(wx)[None], modes, kind)[0]
+
+
+def bps_streams(E, testangles, symbols, N, kind="strict"):
+    """pythran_dsp.py:47-85 for every row of E (nstream, L); returns int32 idx (nstream, L)."""
+    suf, rt, ct = _suf(E.dtype)
+    E = np.ascontiguousarray(E, dtype=ct)
+    testangles = np.atleast_2d(np.asarray(testangles, dtype=rt))
+    comp = np.ascontiguousarray(np.exp(1j * testangles))  # :72, complex of matching width (NumPy>=2)
+    assert comp.dtype == ct
+    symbols = np.ascontiguousarray(symbols, dtype=ct)
+    nstream, L = E.shape
+    idx = np.zeros((nstream, L), dtype=np.int32)
+    rc = getattr(lib(kind), "qo_bps" + suf)(_p(E), nstream, L, L, _p(comp), comp.shape[0],
+                                             comp.shape[1], _p(symbols), symbols.size, N, _p(idx))
+    if rc:
+        raise RuntimeError("oracle bps failed rc=%d" % rc)
+    return idx
+
+
+def bps(E, testangles, symbols, N, kind="strict"):
+    return bps_streams(np.asarray(E)[None], testangles, symbols, N, kind)[0]
+
+
+def select_angles(angles, idx, kind="strict"):
+    """pythran_dsp.py:137-153."""
+    suf, rt, ct = _suf(angles.dtype)
+    angles = np.ascontiguousarray(np.atleast_2d(angles), dtype=rt)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    L = angles.shape[0] if angles.shape[0] > 1 else idx.shape[0]
+    out = np.zeros(L, dtype=rt)
+    getattr(lib(kind), "qo_select_angles" + suf)(_p(angles), angles.shape[0], angles.shape[1],
+                                                 _p(idx), L, _p(out))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# constellations and per-method constants
+# --------------------------------------------------------------------------------------
+def cal_symbols_qam(M):
+    """theory.py:111-178 (square grid, real level slowest; cross constellations relocated)."""
+    nb = int(round(np.log2(M)))
+    if nb % 2 == 0:
+        m = int(round(np.sqrt(M)))
+        lv = np.linspace(-(m - 1), m - 1, m)
+        return (lv[:, None] + 1j * lv[None, :]).flatten()
+    n = (nb - 1) / 2
+    s = 2 ** (n - 1)
+    lr = np.linspace(-(2 ** (n + 1) - 1), 2 ** (n + 1) - 1, int(2 ** (n + 1)))
+    li = np.linspace(-(2 ** n - 1), 2 ** n - 1, int(2 ** n))
+    q = (lr[:, None] + 1j * li[None, :])
+    far = abs(q.real) > 3 * s
+    i1 = far & (abs(q.imag) > s)
+    i2 = far & (abs(q.imag) <= s)
+    q1 = np.sign(q.real) * (abs(q.real) - 2 * s) + 1j * np.sign(q.imag) * (4 * s - abs(q.imag))
+    q2 = np.sign(q.real) * (4 * s - abs(q.real)) + 1j * np.sign(q.imag) * (abs(q.imag) + 2 * s)
+    q = np.where(i1, q1, np.where(i2, q2, q))
+    return q.flatten()
+
+
+def cal_scaling_factor_qam(M):
+    if int(round(np.log2(M))) % 2 == 0:
+        return 2 / 3 * (M - 1)
+    return (abs(cal_symbols_qam(M)) ** 2).mean()
+
+
+def _norm_syms(M):
+    return cal_symbols_qam(M) / np.sqrt(cal_scaling_factor_qam(M))
+
+
+def generate_symbols_for_eq(method, M, dtype):
+    """equalisation.py:101-136 (+ :271-281, :311-359)."""
+    s = _norm_syms(M)
+    if method in ("cma", "cma2", "sgncma"):
+        R = np.mean(abs(s) ** 4) / np.mean(abs(s) ** 2)
+        return np.atleast_2d(R + 0j).astype(dtype)
+    if method == "mcma":
+        R = np.mean(s.real ** 4) / np.mean(s.real ** 2) + 1j * np.mean(s.imag ** 4) / np.mean(s.imag ** 2)
+        return np.atleast_2d(R).astype(dtype)
+    if method == "rde":
+        codes = np.unique(abs(s) ** 4 / abs(s) ** 2)
+        parts = codes[:-1] + np.diff(codes) / 2
+        return np.atleast_2d(np.hstack([codes, parts]) + 0j).astype(dtype)
+    if method == "mrde":
+        cr = np.unique(abs(s.real) ** 4 / abs(s.real) ** 2)
+        ci = np.unique(abs(s.imag) ** 4 / abs(s.imag) ** 2)
+        pr = cr[:-1] + np.diff(cr) / 2
+        pi = ci[:-1] + np.diff(ci) / 2
+        return np.atleast_2d(np.hstack([cr + 1j * ci, pr + 1j * pi])).astype(dtype)
+    if method in ("sbd", "mddma", "dd"):
+        return np.atleast_2d(s).astype(dtype)
+    if method in DATA_AIDED:
+        raise ValueError("%s is a data-aided method and needs the symbols to be passed" % method)
+    raise ValueError("%s is unknown method" % method)
+
+
+def _reshape_symbols(symbols, method, M, dtype, nmodes):
+    """equalisation.py:568-594 (complex-valued methods only)."""
+    if symbols is None or method in NONDECISION_BASED:
+        symbols = generate_symbols_for_eq(method, M, dtype)
+    symbols = np.asarray(symbols)
+    if symbols.ndim == 1 or symbols.shape[0] == 1:
+        symbols = np.tile(symbols, (nmodes, 1))
+    elif symbols.shape[0] != nmodes:
+        raise ValueError("Symbols array is shape {} but signal has {} modes".format(symbols.shape, nmodes))
+    return np.atleast_2d(symbols.astype(dtype))
+
+
+def cal_training_symbol_len(os_, ntaps, L):
+    return int(L // os_ // ntaps - 1) * int(ntaps)  # equalisation.py:361-362
+
+
+def init_taps(ntaps, nmodes, dtype):
+    w = np.zeros((nmodes, nmodes, ntaps), dtype=dtype)  # equalisation.py:364-367
+    for i in range(nmodes):
+        w[i, i, ntaps // 2] = 1
+    return w
+
+
+# --------------------------------------------------------------------------------------
+# L2 drivers
+# --------------------------------------------------------------------------------------
+def apply_filter(E, os_, wxy, modes=None, kind="strict"):
+    """equalisation.py:138-188 (complex taps)."""
+    E = np.copy(E)
+    wxy = np.copy(wxy)
+    modes = np.arange(wxy.shape[0]) if modes is None else np.copy(np.atleast_1d(modes))
+    return apply_filter_to_signal(E, os_, wxy, modes, kind)
+
+
+def equalise_signal(E, os_, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, method="mcma",
+                    adaptive_stepsize=False, symbols=None, modes=None, apply=False,
+                    mu_shared=True, kind="strict", **kwargs):
+    """equalisation.py:468-566."""
+    method = method.lower()
+    E = np.copy(np.asarray(E))
+    mu = E.real.dtype.type(mu)
+    nmodes = E.shape[0]
+    if modes is None:
+        modes = np.arange(nmodes)
+    else:
+        modes = np.atleast_1d(modes)
+        assert np.max(modes) < nmodes, "largest mode number is larger than shape of signal"
+    if wxy is None:
+        wxy = init_taps(Ntaps, nmodes, E.dtype)
+    else:
+        wxy = np.ascontiguousarray(wxy, dtype=E.dtype)
+        Ntaps = wxy.shape[-1]
+        assert wxy.ndim == 3, "wxy needs to be three dimensional"
+        assert wxy.shape[:2] == (nmodes, nmodes)
+    if TrSyms is None:
+        TrSyms = cal_training_symbol_len(os_, Ntaps, E.shape[-1])
+    symbols = _reshape_symbols(symbols, method, M, E.dtype, nmodes)
+    err, wxy, mu = train_equaliser(E, TrSyms, Niter, os_, mu, wxy, modes, adaptive_stepsize,
+                                   symbols.copy(), method, mu_shared, kind)
+    if apply:
+        return apply_filter(E, os_, wxy, modes, kind), wxy, err
+    return wxy, err
+
+
+def dual_mode_equalisation(E, os_, mu, M, wxy=None, Ntaps=None, TrSyms=(None, None), Niter=(1, 1),
+                           methods=("mcma", "sbd"), adaptive_stepsize=(False, False), symbols=None,
+                           modes=None, apply=True, mu_shared=True, kind="strict", **kwargs):
+    """equalisation.py:400-466: stage 2 restarts at sample 0 with the stage-1 taps; the output is
+    the final taps applied to the whole signal."""
+    symbols = np.atleast_1d(symbols)
+    if symbols.ndim < 3:
+        symbols = np.tile(symbols, (2, 1, 1))
+    s0 = None if symbols[0].dtype == object else symbols[0]
+    s1 = None if symbols[1].dtype == object else symbols[1]
+    wxy, err1 = equalise_signal(E, os_, mu[0], M, wxy=wxy, Ntaps=Ntaps, TrSyms=TrSyms[0],
+                                Niter=Niter[0], method=methods[0],
+                                adaptive_stepsize=adaptive_stepsize[0], symbols=s0, modes=modes,
+                                mu_shared=mu_shared, kind=kind)
+    wxy2, err2 = equalise_signal(E, os_, mu[1], M, wxy=wxy, TrSyms=TrSyms[1], Niter=Niter[1],
+                                 method=methods[1], adaptive_stepsize=adaptive_stepsize[1],
+                                 symbols=s1, modes=modes, mu_shared=mu_shared, kind=kind)
+    if apply:
+        return apply_filter(E, os_, wxy2, modes, kind), wxy2, (err1, err2)
+    return wxy2, (err1, err2)
+
+
+def bps_driver(E, Mtestangles, symbols, N, kind="strict"):
+    """phaserecovery.py:141-159: angle table, per-mode index search, unwrap*4/4 on [N:-N],
+    rotate by exp(+1j*ph)."""
+    E = np.asarray(E)
+    dtype = np.float32 if E.dtype == np.dtype(np.complex64) else np.float64
+    angles = np.linspace(-np.pi / 4, np.pi / 4, Mtestangles, endpoint=False, dtype=dtype).reshape(1, -1)
+    Ew = np.atleast_2d(E).astype(E.dtype)
+    ph = []
+    for i in range(Ew.shape[0]):
+        idx = bps(Ew[i], angles, symbols, N, kind)
+        ph.append(select_angles(np.copy(angles), idx.astype(int), kind))
+    ph = np.asarray(ph, dtype=dtype)
+    ph[:, N:-N] = np.unwrap(ph[:, N:-N] * 4) / 4
+    if E.ndim == 1:
+        return (Ew * np.exp(1.j * ph)).flatten(), ph.flatten()
+    return Ew * np.exp(1.j * ph), ph
