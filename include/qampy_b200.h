@@ -1,0 +1,155 @@
+/*
+ * qampy_b200 -- C ABI of the B200-native coherent-receiver DSP hot path.
+ *
+ * This is the drop-in boundary for the ONE path this project re-implements: the adaptive
+ * MIMO FIR equaliser (train + apply) and the blind-phase-search carrier recovery of
+ * ChalmersPhotonicsLab/QAMpy.  Each entry point replaces one Pythran-exported kernel of the
+ * reference (paths relative to the reference checkout):
+ *
+ *   qb_train_equaliser_*        qampy/core/equalisation/pythran_equalisation.py:128-173  train_equaliser
+ *   qb_apply_filter_to_signal_* qampy/core/equalisation/pythran_equalisation.py:33-76    apply_filter_to_signal
+ *   qb_bps_*                    qampy/core/pythran_dsp.py:45-85 bps (+ :26-42 select_angle_index) and,
+ *                               when ph/Eout are requested, the L2 tail
+ *                               qampy/core/phaserecovery.py:150-159 (select_angles, unwrap*4/4, rotate)
+ *   qb_select_angles_*          qampy/core/pythran_dsp.py:133-153 select_angles
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, no C++/torch types.  All functions return 0 on success or a
+ *     negative qb_status; qb_last_error() gives the message of the last failure on the calling
+ *     thread.  Nothing here falls back to a CPU implementation: without a usable CUDA device
+ *     every compute entry point fails with QB_ERR_CUDA.
+ *   - complex arrays are interleaved (re, im) pairs of float (QB_C64) or double (QB_C128),
+ *     row-major, exactly the NumPy layout the reference hands to its kernels.
+ *   - `*_host` entry points take HOST pointers, are synchronous, and do their own H2D/D2H
+ *     copies: they are what a ctypes/cffi binding of the reference's L1 seam calls.
+ *   - `*_dev` entry points take DEVICE pointers (every array argument except `modes`), enqueue
+ *     work on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream) and return
+ *     without synchronising: they are CUDA-graph capturable and keep the signal resident in HBM
+ *     across train -> train -> apply -> bps.
+ *   - batched ("segment") layout: `nseg` independent time segments are processed by one launch.
+ *     Segment s of the signal starts at E + s*seg_stride samples and its mode rows are
+ *     row_stride samples apart, so overlapping segments of one long capture need no copy.
+ *     nseg = 1, seg_stride = nmodes*L, row_stride = L is the reference call.
+ */
+#ifndef QAMPY_B200_H
+#define QAMPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    QB_OK = 0,
+    QB_ERR_ARG = -1,         /* invalid argument (the reference raises ValueError/AssertionError) */
+    QB_ERR_UNSUPPORTED = -2, /* valid in the reference but not implemented here */
+    QB_ERR_CUDA = -3,        /* CUDA runtime/driver error, or no device */
+    QB_ERR_NOMEM = -4
+} qb_status;
+
+typedef enum { QB_C64 = 0, QB_C128 = 1 } qb_dtype;
+
+/* error functions, pythran_equalisation.py:131-152 (string dispatch) */
+typedef enum {
+    QB_CMA = 0,      /* :178 cma_error        */
+    QB_CMA2 = 1,     /* :182 cma2_error       */
+    QB_SGNCMA = 2,   /* :133-134 mapped to cma_error by the reference */
+    QB_MCMA = 3,     /* :190 mcma_error       */
+    QB_RDE = 4,      /* :196 rde_error        */
+    QB_MRDE = 5,     /* :203 mrde_error       */
+    QB_SBD = 6,      /* :213 sbd_error        */
+    QB_SBD_DATA = 7, /* :218 sbd_data_error   */
+    QB_MDDMA = 8,    /* :224 mddma_error      */
+    QB_DD = 9        /* :229 ddlms_error      */
+} qb_method;
+
+#define QB_MAX_MODES 8     /* nmodes (input rows / output modes) per segment            */
+#define QB_MAX_TAPDIM 512  /* nmodes * ntaps handled by the trainer                     */
+#define QB_MAX_ANGLES 256  /* BPS test angles                                           */
+
+int qb_version(void);
+const char *qb_last_error(void);
+/* number of CUDA devices visible, or a negative qb_status */
+int qb_device_count(void);
+/* method name ("mcma", "mrde", ...) -> qb_method, or QB_ERR_ARG ("Unknown method") */
+int qb_method_from_name(const char *name);
+
+/* ---- equaliser training ---------------------------------------------------------------
+ * replaces train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, method)
+ *   E        (nseg, nmodes, >= (TrSyms-1)*os + ntaps) complex
+ *   wx       (nseg, nmodes, nmodes, ntaps) complex, IN/OUT (the reference updates wx in place)
+ *   modes    HOST array of nsel output-mode numbers (< nmodes)
+ *   symbols  (nmodes, K) complex per-method constants / alphabet / training sequence
+ *   mu       (nseg, nsel) real, IN/OUT: step size per trained stream (final value written back)
+ *   err      (nseg, nmodes, TrSyms*Niter) complex or NULL; only rows of selected modes are written
+ * Each (segment, mode) stream is an independent serial recurrence.                         */
+int qb_train_equaliser_dev(int dtype, const void *E, int64_t nseg, int64_t seg_stride,
+                           int64_t row_stride, int64_t nmodes, int64_t TrSyms, int64_t Niter,
+                           int64_t os, void *wx, int64_t ntaps, const int64_t *modes, int64_t nsel,
+                           int adaptive, const void *symbols, int64_t K, int method, void *mu,
+                           void *err, void *stream);
+
+/* HOST-pointer form with the reference's exact call shape (nseg = 1).  `mu` points to ONE real
+ * (in: step size, out: final step size).  mu_shared != 0 reproduces the interpreted reference,
+ * where one mu is carried through the modes in list order when adaptive (:130, :162-172);
+ * mu_shared == 0 starts every mode from *mu (deterministic; what an OpenMP build intends).   */
+int qb_train_equaliser_host(int dtype, const void *E, int64_t nmodes, int64_t L, int64_t TrSyms,
+                            int64_t Niter, int64_t os, void *mu, void *wx, int64_t ntaps,
+                            const int64_t *modes, int64_t nsel, int adaptive, const void *symbols,
+                            int64_t K, int method, int mu_shared, void *err);
+
+/* ---- static filter + decimation ---------------------------------------------------------
+ * replaces apply_filter_to_signal(E, os, wx, modes):  out (nseg, nsel, N), N = (L-ntaps+1)/os */
+int qb_apply_filter_to_signal_dev(int dtype, const void *E, int64_t nseg, int64_t seg_stride,
+                                  int64_t row_stride, int64_t nmodes, int64_t L, int64_t os,
+                                  const void *wx, int64_t ntaps, const int64_t *modes, int64_t nsel,
+                                  void *out, void *stream);
+int qb_apply_filter_to_signal_host(int dtype, const void *E, int64_t nmodes, int64_t L, int64_t os,
+                                   const void *wx, int64_t ntaps, const int64_t *modes,
+                                   int64_t nsel, void *out);
+
+/* ---- blind phase search -------------------------------------------------------------------
+ * replaces bps(E, testangles, symbols, N) for `nstream` independent 1-D streams (the reference
+ * is called once per polarisation) and optionally the L2 tail.
+ *   E        (nstream, L) complex, stream s at E + s*stream_stride
+ *   comp     (A) complex  = exp(1j*testangles)   (pythran_dsp.py:72; computed by the caller so the
+ *                                                 table is bit-identical to NumPy's)
+ *   angles   (A) real test angles (only read when ph/Eout are requested)
+ *   symbols  (M) complex alphabet
+ *   lev_re/lev_im  sorted, uniformly spaced per-axis levels when the alphabet is a full
+ *            rectangular grid (see qb_detect_grid_host), else n_re = n_im = 0 -> brute force.
+ *            The slicer result is bit-identical to the brute-force minimum distance.
+ *   idx      (nstream, L) int32 or NULL   -- select_angle_index output (edges 0)
+ *   ph       (nstream, L) real  or NULL   -- angles[idx], [N:L-N] unwrapped as np.unwrap(ph*4)/4
+ *   Eout     (nstream, L) complex or NULL -- E * exp(+1j*ph)
+ * Only a single angle table (testangles.shape[0] == 1) is supported.                          */
+int qb_bps_dev(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
+               const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
+               const void *lev_re, int64_t n_re, const void *lev_im, int64_t n_im, int64_t N,
+               int32_t *idx, void *ph, void *Eout, void *stream);
+int qb_bps_host(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp,
+                const void *angles, int64_t A, const void *symbols, int64_t M, int64_t N,
+                int32_t *idx, void *ph, void *Eout);
+
+/* HOST helper: if `symbols` (M complex) is exactly the product set of n_re real levels and n_im
+ * imaginary levels (each uniformly spaced), write the sorted levels (capacity 64 each, real type
+ * of dtype) and return 1; return 0 if not a grid; negative on error.                          */
+int qb_detect_grid_host(int dtype, const void *symbols, int64_t M, void *lev_re, int64_t *n_re,
+                        void *lev_im, int64_t *n_im);
+
+/* ---- select_angles(angles, idx): out[i] = angles[p > 1 ? i : 0][idx[i]] ----------------------- */
+int qb_select_angles_dev(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
+                         int64_t L, void *out, void *stream);
+int qb_select_angles_host(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
+                          int64_t L, void *out);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t qb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QAMPY_B200_H */

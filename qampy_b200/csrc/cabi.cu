@@ -1,0 +1,422 @@
+// C ABI of qampy_b200 (see include/qampy_b200.h): argument validation, error strings, the
+// device-pointer entry points (thin launch wrappers) and the host-pointer entry points (own H2D /
+// D2H copies around the same launches).  No CPU fallback exists anywhere in this file: without a
+// CUDA device every compute entry point returns QB_ERR_CUDA.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "qb_common.cuh"
+
+namespace qb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+int apply_dispatch(int dtype, const void *E, int64_t nseg, int64_t seg_stride, int64_t row_stride,
+                   int64_t nmodes, int64_t L, int64_t os, const void *wx, int64_t ntaps,
+                   const int64_t *modes, int64_t nsel, void *out, cudaStream_t st);
+int train_dispatch(int dtype, const void *E, int64_t nseg, int64_t seg_stride, int64_t row_stride,
+                   int64_t nmodes, int64_t TrSyms, int64_t Niter, int64_t os, void *wx, int64_t ntaps,
+                   const int64_t *modes, int64_t nsel, int adaptive, const void *symbols, int64_t K,
+                   int method, void *mu, void *err, cudaStream_t st);
+int bps_dispatch(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
+                 const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
+                 const void *lev_re, int64_t n_re, const void *lev_im, int64_t n_im, int64_t N,
+                 int32_t *idx, void *ph, void *Eout, cudaStream_t st);
+int select_angles_dispatch(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
+                           int64_t L, void *out, cudaStream_t st);
+
+static inline size_t csize(int dtype) { return dtype == QB_C64 ? 8 : 16; }
+static inline size_t rsize(int dtype) { return dtype == QB_C64 ? 4 : 8; }
+
+static int check_dtype(int dtype)
+{
+    if (dtype != QB_C64 && dtype != QB_C128)
+        return set_error(QB_ERR_ARG, "dtype must be QB_C64 or QB_C128, got %d", dtype);
+    return QB_OK;
+}
+
+static int check_modes(const int64_t *modes, int64_t nsel, int64_t nmodes)
+{
+    QB_REQUIRE(nmodes >= 1 && nmodes <= QB_MAX_MODES, "nmodes must be in [1, %d], got %lld", QB_MAX_MODES,
+               (long long)nmodes);
+    QB_REQUIRE(nsel >= 0 && nsel <= QB_MAX_MODES, "number of selected modes must be in [0, %d]", QB_MAX_MODES);
+    QB_REQUIRE(nsel == 0 || modes != nullptr, "modes must not be NULL");
+    for (int64_t j = 0; j < nsel; j++)
+        QB_REQUIRE(modes[j] >= 0 && modes[j] < nmodes,
+                   "Maximum mode number must not be higher than number of modes (mode %lld, nmodes %lld)",
+                   (long long)modes[j], (long long)nmodes);
+    return QB_OK;
+}
+
+// scratch device buffer that frees itself; stream-ordered pool allocations (cached by the driver)
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    int alloc(size_t bytes)
+    {
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, st);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return set_error(e == cudaErrorMemoryAllocation ? QB_ERR_NOMEM : QB_ERR_CUDA,
+                             "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        return QB_OK;
+    }
+    ~DevBuf()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+
+static int host_stream(cudaStream_t *st)
+{
+    static cudaStream_t s = nullptr;
+    static bool pool_done = false;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_error(QB_ERR_CUDA, "no CUDA device available (%s); qampy_b200 has no CPU fallback",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (!s) QB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    if (!pool_done) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        QB_CUDA_CHECK(cudaGetDevice(&dev));
+        QB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thr = ~0ull;  // keep freed scratch cached between calls
+        QB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        pool_done = true;
+    }
+    *st = s;
+    return QB_OK;
+}
+
+#define QB_TRY(expr)             \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != QB_OK) return _rc; \
+    } while (0)
+
+template <typename T>
+static int detect_grid(const T *sy, int64_t M, T *lre, int64_t *n_re, T *lim, int64_t *n_im)
+{
+    std::vector<T> re, im;
+    for (int64_t j = 0; j < M; j++) {
+        bool fr = false, fi = false;
+        for (T v : re) fr = fr || v == sy[2 * j];
+        for (T v : im) fi = fi || v == sy[2 * j + 1];
+        if (!fr) re.push_back(sy[2 * j]);
+        if (!fi) im.push_back(sy[2 * j + 1]);
+        if (re.size() > 64 || im.size() > 64) return 0;
+    }
+    if ((int64_t)(re.size() * im.size()) != M) return 0;
+    auto sortv = [](std::vector<T> &v) {
+        for (size_t a = 1; a < v.size(); a++)
+            for (size_t b = a; b > 0 && v[b] < v[b - 1]; b--) {
+                T t = v[b];
+                v[b] = v[b - 1];
+                v[b - 1] = t;
+            }
+    };
+    sortv(re);
+    sortv(im);
+    // every (re, im) combination must be present exactly once
+    for (T a : re)
+        for (T b : im) {
+            int cnt = 0;
+            for (int64_t j = 0; j < M; j++) cnt += (sy[2 * j] == a && sy[2 * j + 1] == b);
+            if (cnt != 1) return 0;
+        }
+    auto uniform = [](const std::vector<T> &v) {
+        if (v.size() < 2) return true;
+        const double step = ((double)v.back() - (double)v.front()) / (double)(v.size() - 1);
+        if (!(step > 0) || !isfinite(step)) return false;
+        for (size_t a = 0; a < v.size(); a++)
+            if (fabs((double)v[a] - ((double)v.front() + step * (double)a)) > 1e-3 * step) return false;
+        return true;
+    };
+    if (!uniform(re) || !uniform(im)) return 0;
+    for (T v : re)
+        if (!isfinite((double)v)) return 0;
+    for (T v : im)
+        if (!isfinite((double)v)) return 0;
+    for (size_t a = 0; a < re.size(); a++) lre[a] = re[a];
+    for (size_t a = 0; a < im.size(); a++) lim[a] = im[a];
+    *n_re = (int64_t)re.size();
+    *n_im = (int64_t)im.size();
+    return 1;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int qb_version(void) { return QB_VERSION; }
+const char *qb_last_error(void) { return g_err; }
+int64_t qb_launch_count(void) { return g_launches.load(); }
+
+int qb_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return set_error(QB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int qb_method_from_name(const char *name)
+{
+    static const char *names[] = {"cma", "cma2", "sgncma", "mcma", "rde", "mrde", "sbd", "sbd_data", "mddma", "dd"};
+    if (name)
+        for (int i = 0; i < 10; i++)
+            if (strcmp(name, names[i]) == 0) return i;
+    return set_error(QB_ERR_ARG, "Unknown method %s", name ? name : "(null)");
+}
+
+static int train_check(int dtype, const void *E, int64_t nseg, int64_t nmodes, int64_t TrSyms, int64_t Niter,
+                       int64_t os, const void *wx, int64_t ntaps, const int64_t *modes, int64_t nsel,
+                       const void *symbols, int64_t K, int method, const void *mu)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(method >= QB_CMA && method <= QB_DD, "Unknown method %d", method);
+    QB_REQUIRE(E && wx && symbols && mu, "E, wx, symbols and mu must not be NULL");
+    QB_REQUIRE(nseg >= 0 && TrSyms >= 0 && Niter >= 0, "nseg, TrSyms and Niter must be non-negative");
+    QB_REQUIRE(os >= 1, "oversampling factor must be larger than 0");
+    QB_REQUIRE(ntaps >= 1, "ntaps must be >= 1");
+    QB_TRY(check_modes(modes, nsel, nmodes));
+    QB_REQUIRE(K >= 1, "symbols must hold at least one value per mode");
+    QB_REQUIRE(method != QB_SBD_DATA || K >= TrSyms, "sbd_data needs at least TrSyms training symbols per mode");
+    if (nmodes * ntaps > QB_MAX_TAPDIM)
+        return set_error(QB_ERR_UNSUPPORTED, "nmodes*ntaps = %lld exceeds %d", (long long)(nmodes * ntaps),
+                         QB_MAX_TAPDIM);
+    return QB_OK;
+}
+
+int qb_train_equaliser_dev(int dtype, const void *E, int64_t nseg, int64_t seg_stride, int64_t row_stride,
+                           int64_t nmodes, int64_t TrSyms, int64_t Niter, int64_t os, void *wx, int64_t ntaps,
+                           const int64_t *modes, int64_t nsel, int adaptive, const void *symbols, int64_t K,
+                           int method, void *mu, void *err, void *stream)
+{
+    QB_TRY(train_check(dtype, E, nseg, nmodes, TrSyms, Niter, os, wx, ntaps, modes, nsel, symbols, K, method, mu));
+    return train_dispatch(dtype, E, nseg, seg_stride, row_stride, nmodes, TrSyms, Niter, os, wx, ntaps, modes,
+                          nsel, adaptive, symbols, K, method, mu, err, (cudaStream_t)stream);
+}
+
+int qb_train_equaliser_host(int dtype, const void *E, int64_t nmodes, int64_t L, int64_t TrSyms, int64_t Niter,
+                            int64_t os, void *mu, void *wx, int64_t ntaps, const int64_t *modes, int64_t nsel,
+                            int adaptive, const void *symbols, int64_t K, int method, int mu_shared, void *err)
+{
+    QB_TRY(train_check(dtype, E, 1, nmodes, TrSyms, Niter, os, wx, ntaps, modes, nsel, symbols, K, method, mu));
+    QB_REQUIRE(TrSyms == 0 || (TrSyms - 1) * os + ntaps <= L,
+               "Field must be longer than the number of training symbols");
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    const size_t cs = csize(dtype), rs = rsize(dtype);
+    const size_t nE = (size_t)nmodes * L, nW = (size_t)nmodes * nmodes * ntaps, nS = (size_t)nmodes * K;
+    const size_t nErr = (size_t)nmodes * TrSyms * Niter;
+    DevBuf dE(st), dW(st), dS(st), dMu(st), dErr(st);
+    QB_TRY(dE.alloc(nE * cs));
+    QB_TRY(dW.alloc(nW * cs));
+    QB_TRY(dS.alloc(nS * cs));
+    QB_TRY(dMu.alloc(QB_MAX_MODES * rs));
+    if (err) QB_TRY(dErr.alloc(nErr * cs));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dE.p, E, nE * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dW.p, wx, nW * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dS.p, symbols, nS * cs, cudaMemcpyHostToDevice, st));
+    if (err) QB_CUDA_CHECK(cudaMemsetAsync(dErr.p, 0, nErr * cs, st));  // unselected rows stay 0 (:161)
+    unsigned char mubuf[QB_MAX_MODES * 8];
+    if (!adaptive || !mu_shared || nsel <= 1) {
+        for (int64_t j = 0; j < nsel; j++) memcpy(mubuf + j * rs, mu, rs);
+        QB_CUDA_CHECK(cudaMemcpyAsync(dMu.p, mubuf, (nsel ? nsel : 1) * rs, cudaMemcpyHostToDevice, st));
+        QB_TRY(train_dispatch(dtype, dE.p, 1, nE, L, nmodes, TrSyms, Niter, os, dW.p, ntaps, modes, nsel, adaptive,
+                              dS.p, K, method, dMu.p, err ? dErr.p : nullptr, st));
+        if (nsel > 0)
+            QB_CUDA_CHECK(cudaMemcpyAsync(mu, (char *)dMu.p + (nsel - 1) * rs, rs, cudaMemcpyDeviceToHost, st));
+    } else {
+        // interpreted-reference semantics: one mu carried through the modes in list order; the device
+        // keeps mu, so mode j+1 simply starts from the slot mode j finished in
+        QB_CUDA_CHECK(cudaMemcpyAsync(dMu.p, mu, rs, cudaMemcpyHostToDevice, st));
+        for (int64_t j = 0; j < nsel; j++)
+            QB_TRY(train_dispatch(dtype, dE.p, 1, nE, L, nmodes, TrSyms, Niter, os, dW.p, ntaps, modes + j, 1,
+                                  adaptive, dS.p, K, method, dMu.p, err ? dErr.p : nullptr, st));
+        QB_CUDA_CHECK(cudaMemcpyAsync(mu, dMu.p, rs, cudaMemcpyDeviceToHost, st));
+    }
+    QB_CUDA_CHECK(cudaMemcpyAsync(wx, dW.p, nW * cs, cudaMemcpyDeviceToHost, st));
+    if (err) QB_CUDA_CHECK(cudaMemcpyAsync(err, dErr.p, nErr * cs, cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
+}
+
+static int apply_check(int dtype, const void *E, int64_t nseg, int64_t nmodes, int64_t L, int64_t os,
+                       const void *wx, int64_t ntaps, const int64_t *modes, int64_t nsel, const void *out)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(os >= 1, "oversampling factor must be larger than 0");
+    QB_REQUIRE(ntaps >= 1 && L >= 0 && nseg >= 0, "ntaps must be >= 1 and L, nseg non-negative");
+    QB_TRY(check_modes(modes, nsel, nmodes));
+    const int64_t N = (L - ntaps + 1) / os;
+    QB_REQUIRE(N <= 0 || nsel == 0 || nseg == 0 || (E && wx && out), "E, wx and out must not be NULL");
+    return QB_OK;
+}
+
+int qb_apply_filter_to_signal_dev(int dtype, const void *E, int64_t nseg, int64_t seg_stride, int64_t row_stride,
+                                  int64_t nmodes, int64_t L, int64_t os, const void *wx, int64_t ntaps,
+                                  const int64_t *modes, int64_t nsel, void *out, void *stream)
+{
+    QB_TRY(apply_check(dtype, E, nseg, nmodes, L, os, wx, ntaps, modes, nsel, out));
+    return apply_dispatch(dtype, E, nseg, seg_stride, row_stride, nmodes, L, os, wx, ntaps, modes, nsel, out,
+                          (cudaStream_t)stream);
+}
+
+int qb_apply_filter_to_signal_host(int dtype, const void *E, int64_t nmodes, int64_t L, int64_t os,
+                                   const void *wx, int64_t ntaps, const int64_t *modes, int64_t nsel, void *out)
+{
+    QB_TRY(apply_check(dtype, E, 1, nmodes, L, os, wx, ntaps, modes, nsel, out));
+    const int64_t N = (L - ntaps + 1) / os;
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    if (N <= 0 || nsel == 0) return QB_OK;
+    const size_t cs = csize(dtype);
+    const size_t nE = (size_t)nmodes * L, nW = (size_t)nmodes * nmodes * ntaps, nO = (size_t)nsel * N;
+    DevBuf dE(st), dW(st), dO(st);
+    QB_TRY(dE.alloc(nE * cs));
+    QB_TRY(dW.alloc(nW * cs));
+    QB_TRY(dO.alloc(nO * cs));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dE.p, E, nE * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dW.p, wx, nW * cs, cudaMemcpyHostToDevice, st));
+    QB_TRY(apply_dispatch(dtype, dE.p, 1, nE, L, nmodes, L, os, dW.p, ntaps, modes, nsel, dO.p, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(out, dO.p, nO * cs, cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
+}
+
+static int bps_check(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp, const void *angles,
+                     int64_t A, const void *symbols, int64_t M, int64_t n_re, int64_t n_im, int64_t N,
+                     const void *ph, const void *Eout)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(nstream >= 0 && L >= 0, "nstream and L must be non-negative");
+    QB_REQUIRE(A >= 1 && A <= QB_MAX_ANGLES, "number of test angles must be in [1, %d], got %lld", QB_MAX_ANGLES,
+               (long long)A);
+    QB_REQUIRE(N >= 1, "averaging block length N must be >= 1");
+    QB_REQUIRE(M >= 1 && symbols, "the symbol alphabet must not be empty");
+    QB_REQUIRE(E && comp, "E and comp must not be NULL");
+    QB_REQUIRE((n_re == 0) == (n_im == 0) && n_re >= 0 && n_re <= 64 && n_im <= 64, "invalid slicer levels");
+    QB_REQUIRE(n_re == 0 || n_re * n_im == M, "slicer levels do not match the alphabet size");
+    QB_REQUIRE(!Eout || ph, "Eout requires ph");
+    QB_REQUIRE(!ph || angles, "ph requires the angle table");
+    return QB_OK;
+}
+
+int qb_bps_dev(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L, const void *comp,
+               const void *angles, int64_t A, const void *symbols, int64_t M, const void *lev_re, int64_t n_re,
+               const void *lev_im, int64_t n_im, int64_t N, int32_t *idx, void *ph, void *Eout, void *stream)
+{
+    QB_TRY(bps_check(dtype, E, nstream, L, comp, angles, A, symbols, M, n_re, n_im, N, ph, Eout));
+    return bps_dispatch(dtype, E, nstream, stream_stride, L, comp, angles, A, symbols, M, lev_re, n_re, lev_im,
+                        n_im, N, idx, ph, Eout, (cudaStream_t)stream);
+}
+
+int qb_detect_grid_host(int dtype, const void *symbols, int64_t M, void *lev_re, int64_t *n_re, void *lev_im,
+                        int64_t *n_im)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(symbols && lev_re && lev_im && n_re && n_im && M >= 1, "invalid arguments");
+    *n_re = *n_im = 0;
+    if (dtype == QB_C64)
+        return detect_grid<float>((const float *)symbols, M, (float *)lev_re, n_re, (float *)lev_im, n_im);
+    return detect_grid<double>((const double *)symbols, M, (double *)lev_re, n_re, (double *)lev_im, n_im);
+}
+
+int qb_bps_host(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp, const void *angles,
+                int64_t A, const void *symbols, int64_t M, int64_t N, int32_t *idx, void *ph, void *Eout)
+{
+    QB_TRY(bps_check(dtype, E, nstream, L, comp, angles, A, symbols, M, 0, 0, N, ph, Eout));
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    if (nstream == 0 || L == 0) return QB_OK;
+    const size_t cs = csize(dtype), rs = rsize(dtype);
+    unsigned char lre[64 * 8], lim[64 * 8];
+    int64_t n_re = 0, n_im = 0;
+    const int grid = qb_detect_grid_host(dtype, symbols, M, lre, &n_re, lim, &n_im);
+    if (grid < 0) return grid;
+    if (grid == 0) n_re = n_im = 0;
+    const size_t nE = (size_t)nstream * L;
+    DevBuf dE(st), dC(st), dA(st), dS(st), dLr(st), dLi(st), dI(st), dP(st), dO(st);
+    QB_TRY(dE.alloc(nE * cs));
+    QB_TRY(dC.alloc(A * cs));
+    QB_TRY(dA.alloc(A * rs));
+    QB_TRY(dS.alloc(M * cs));
+    QB_TRY(dLr.alloc(64 * rs));
+    QB_TRY(dLi.alloc(64 * rs));
+    if (idx) QB_TRY(dI.alloc(nE * sizeof(int32_t)));
+    if (ph) QB_TRY(dP.alloc(nE * rs));
+    if (Eout) QB_TRY(dO.alloc(nE * cs));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dE.p, E, nE * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dC.p, comp, A * cs, cudaMemcpyHostToDevice, st));
+    if (angles) QB_CUDA_CHECK(cudaMemcpyAsync(dA.p, angles, A * rs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dS.p, symbols, M * cs, cudaMemcpyHostToDevice, st));
+    if (n_re) {
+        QB_CUDA_CHECK(cudaMemcpyAsync(dLr.p, lre, n_re * rs, cudaMemcpyHostToDevice, st));
+        QB_CUDA_CHECK(cudaMemcpyAsync(dLi.p, lim, n_im * rs, cudaMemcpyHostToDevice, st));
+    }
+    QB_TRY(bps_dispatch(dtype, dE.p, nstream, L, L, dC.p, angles ? dA.p : nullptr, A, dS.p, M, dLr.p, n_re, dLi.p,
+                        n_im, N, idx ? (int32_t *)dI.p : nullptr, ph ? dP.p : nullptr, Eout ? dO.p : nullptr, st));
+    if (idx) QB_CUDA_CHECK(cudaMemcpyAsync(idx, dI.p, nE * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (ph) QB_CUDA_CHECK(cudaMemcpyAsync(ph, dP.p, nE * rs, cudaMemcpyDeviceToHost, st));
+    if (Eout) QB_CUDA_CHECK(cudaMemcpyAsync(Eout, dO.p, nE * cs, cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
+}
+
+int qb_select_angles_dev(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx, int64_t L,
+                         void *out, void *stream)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(angles && idx && out && A >= 1 && p >= 1 && L >= 0, "invalid arguments");
+    return select_angles_dispatch(dtype, angles, p, A, idx, L, out, (cudaStream_t)stream);
+}
+
+int qb_select_angles_host(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx, int64_t L,
+                          void *out)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(A >= 1 && p >= 1 && L >= 0, "invalid arguments");
+    QB_REQUIRE(L == 0 || (angles && idx && out), "angles, idx and out must not be NULL");
+    for (int64_t i = 0; i < L; i++)
+        QB_REQUIRE(idx[i] >= 0 && idx[i] < A, "angle index out of range at %lld", (long long)i);
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    if (L == 0) return QB_OK;
+    const size_t rs = rsize(dtype);
+    DevBuf dA(st), dI(st), dO(st);
+    QB_TRY(dA.alloc((size_t)p * A * rs));
+    QB_TRY(dI.alloc((size_t)L * sizeof(int64_t)));
+    QB_TRY(dO.alloc((size_t)L * rs));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dA.p, angles, (size_t)p * A * rs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dI.p, idx, (size_t)L * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    QB_TRY(select_angles_dispatch(dtype, dA.p, p, A, (const int64_t *)dI.p, L, dO.p, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(out, dO.p, (size_t)L * rs, cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+// Shared device/host helpers for the qampy_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/qampy_b200.h"
+
+namespace qb {
+
+// ---- error plumbing (host) -----------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define QB_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return qb::set_error(QB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    } while (0)
+
+#define QB_REQUIRE(cond, ...)                                                                \
+    do {                                                                                     \
+        if (!(cond))                                                                         \
+            return qb::set_error(QB_ERR_ARG, __VA_ARGS__);                                   \
+    } while (0)
+
+// ---- complex scalar type -------------------------------------------------------------------
+template <typename T>
+struct cx_t;
+template <>
+struct cx_t<float> {
+    using type = float2;
+};
+template <>
+struct cx_t<double> {
+    using type = double2;
+};
+template <typename T>
+using cx = typename cx_t<T>::type;
+
+template <typename T>
+__host__ __device__ __forceinline__ cx<T> make_cx(T re, T im)
+{
+    cx<T> r;
+    r.x = re;
+    r.y = im;
+    return r;
+}
+
+// Unfused IEEE ops: the BPS distance contract forbids FMA contraction.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+template <typename T>
+__device__ __forceinline__ T shfl_xor(T v, int m)
+{
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+template <typename T>
+__device__ __forceinline__ T shfl_idx(T v, int l)
+{
+    return __shfl_sync(0xffffffffu, v, l);
+}
+
+// ---- async copy (LDGSTS) and TMA bulk copy (UBLKCP) + mbarrier -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem)
+{
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(smem)), "l"(gmem),
+                 "n"(BYTES));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared::cta, completion on an mbarrier.  Needs 16-byte aligned
+// source, destination and size.
+__device__ __forceinline__ void tma_bulk_g2s(void *smem, const void *gmem, uint32_t bytes,
+                                             uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+            "r"(smem_u32(smem)),
+        "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+struct ModeList {
+    int n;
+    int m[QB_MAX_MODES];
+};
+
+}  // namespace qb

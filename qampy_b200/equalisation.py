@@ -1,0 +1,141 @@
+"""L2 drop-in for ``qampy/core/equalisation/equalisation.py``: ``equalise_signal`` (:468-566),
+``dual_mode_equalisation`` (:400-466) and ``apply_filter`` (:138-188) with the same signatures,
+return tuples and error behaviour, but with the signal resident in HBM across
+train -> train -> apply (one H2D copy of ``E``, no intermediate round trips).
+
+Host work that stays in NumPy is exactly the reference's own glue: per-method constant tables,
+default training length, tap initialisation (see ``qampy_b200/theory.py``).
+"""
+import numpy as np
+import torch
+
+from . import _lib, device, theory
+from .theory import (DATA_AIDED, DECISION_BASED, NONDECISION_BASED, REAL_VALUED,  # noqa: F401 (API parity)
+                     TRAINING_FCTS)
+
+
+def _dev():
+    _lib.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _check_complex(E):
+    E = np.asarray(E)
+    if E.dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+        raise TypeError("qampy_b200 equalises complex64/complex128 signals, got %s" % E.dtype)
+    return E
+
+
+def _to_dev(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+
+
+def apply_filter(E, os, wxy, method="pyt", modes=None):
+    """Apply the equaliser taps to the signal (decimating by ``os``)."""
+    if method not in ("pyt", "py", "cuda"):
+        raise NotImplementedError("Only py and pythran methods are implemented")
+    E = _check_complex(E)
+    wxy = np.asarray(wxy)
+    if not np.iscomplexobj(wxy):
+        raise NotImplementedError("real-valued taps are not part of the CUDA hot path")
+    dev = _dev()
+    modes = np.arange(wxy.shape[0]) if modes is None else np.copy(np.atleast_1d(modes))
+    assert np.max(modes) < wxy.shape[0], "largest mode number is larger than shape of signal"
+    Ed = _to_dev(np.atleast_2d(E), dev)[None]
+    wd = _to_dev(wxy.astype(E.dtype), dev)[None]
+    out = device.apply_filter_to_signal(Ed, int(os), wd, modes)
+    return out[0].cpu().numpy()
+
+
+def _train_stage(Ed, os, mu, M, wd, ntaps, TrSyms, Niter, method, adaptive, symbols, modes, cdtype,
+                 mu_shared=True):
+    """One equalise_signal training stage on device tensors (nseg = 1).  Returns err (numpy)."""
+    dev = Ed.device
+    nmodes, L = Ed.shape[1], Ed.shape[2]
+    rt = np.float32 if cdtype == np.complex64 else np.float64
+    if TrSyms is None:
+        TrSyms = theory.cal_training_symbol_len(os, ntaps, L)
+    symbols = theory.reshape_symbols(symbols, method, M, cdtype, nmodes)
+    sd = _to_dev(symbols, dev)
+    err = torch.zeros((1, nmodes, TrSyms * Niter), dtype=Ed.dtype, device=dev)
+    mu = rt(mu)
+    if adaptive and mu_shared and len(modes) > 1:
+        # the reference carries ONE step size through the modes in list order when interpreted
+        mud = torch.full((1, 1), float(mu), dtype=device._REAL[Ed.dtype], device=dev)
+        for m in modes:
+            device.train_equaliser(Ed, TrSyms, Niter, os, mud, wd, [m], adaptive, sd, method, err)
+    else:
+        mud = torch.full((1, len(modes)), float(mu), dtype=device._REAL[Ed.dtype], device=dev)
+        device.train_equaliser(Ed, TrSyms, Niter, os, mud, wd, modes, adaptive, sd, method, err)
+    return err
+
+
+def _prepare(E, wxy, Ntaps, modes, method):
+    method = method.lower()
+    if method in REAL_VALUED:
+        raise NotImplementedError("real-valued equaliser methods (%s) are not part of the CUDA hot path" % method)
+    if method not in _lib.METHODS:
+        raise ValueError("Unknown method %s" % method)
+    E = np.atleast_2d(_check_complex(E))
+    nmodes = E.shape[0]
+    if modes is None:
+        modes = np.arange(nmodes)
+    else:
+        modes = np.atleast_1d(modes)
+        assert np.max(modes) < nmodes, "largest mode number is larger than shape of signal"
+    wxy_user = None
+    if wxy is None:
+        wxy = theory.init_taps(Ntaps, nmodes, E.dtype)
+    else:
+        wxy_user = wxy
+        wxy = np.ascontiguousarray(wxy, dtype=E.dtype)
+        Ntaps = wxy.shape[-1]
+        assert wxy.ndim == 3, "wxy needs to be three dimensional"
+        assert wxy.shape[:2] == (nmodes, nmodes), "The first 2 dimensions of wxy need to be the same shape as E"
+    return method, E, nmodes, modes, wxy, wxy_user, Ntaps
+
+
+def equalise_signal(E, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, method="mcma",
+                    adaptive_stepsize=False, symbols=None, modes=None, apply=False, **kwargs):
+    """Blind equalisation with one training method; see the reference docstring for the arguments.
+    Returns ``(E_out,) wxy, err``.  A user-supplied ``wxy`` that is already a C-contiguous array of
+    the signal's dtype is trained in place, as in the reference (:547)."""
+    method, E, nmodes, modes, wxy, wxy_user, Ntaps = _prepare(E, wxy, Ntaps, modes, method)
+    dev = _dev()
+    Ed = _to_dev(E, dev)[None]
+    wd = _to_dev(wxy, dev)[None].contiguous()
+    err = _train_stage(Ed, int(os), mu, M, wd, Ntaps, TrSyms, int(Niter), method, adaptive_stepsize, symbols,
+                       modes, E.dtype, kwargs.get("mu_shared", True))
+    out = device.apply_filter_to_signal(Ed, int(os), wd, modes) if apply else None
+    np.copyto(wxy, wd[0].cpu().numpy())
+    err = err[0].cpu().numpy()
+    if apply:
+        return out[0].cpu().numpy(), wxy, err
+    return wxy, err
+
+
+def dual_mode_equalisation(E, os, mu, M, wxy=None, Ntaps=None, TrSyms=(None, None), Niter=(1, 1),
+                           methods=("mcma", "sbd"), adaptive_stepsize=(False, False), symbols=None,
+                           modes=None, apply=True, **kwargs):
+    """Two-stage blind equalisation: stage 2 restarts at sample 0 with the stage-1 taps and the
+    returned signal is the final taps applied to the whole input (:460-464)."""
+    symbols = np.atleast_1d(symbols)
+    if symbols.ndim < 3:
+        symbols = np.tile(symbols, (2, 1, 1))
+    sy = [None if symbols[i].dtype == object else symbols[i] for i in range(2)]
+    m0, E, nmodes, modes, wxy, wxy_user, Ntaps = _prepare(E, wxy, Ntaps, modes, methods[0])
+    m1 = _prepare(E, wxy, None, modes, methods[1])[0]
+    dev = _dev()
+    Ed = _to_dev(E, dev)[None]
+    wd = _to_dev(wxy, dev)[None].contiguous()
+    shared = kwargs.get("mu_shared", True)
+    err1 = _train_stage(Ed, int(os), mu[0], M, wd, Ntaps, TrSyms[0], int(Niter[0]), m0, adaptive_stepsize[0],
+                        sy[0], modes, E.dtype, shared)
+    err2 = _train_stage(Ed, int(os), mu[1], M, wd, Ntaps, TrSyms[1], int(Niter[1]), m1, adaptive_stepsize[1],
+                        sy[1], modes, E.dtype, shared)
+    out = device.apply_filter_to_signal(Ed, int(os), wd, modes) if apply else None
+    np.copyto(wxy, wd[0].cpu().numpy())
+    errs = (err1[0].cpu().numpy(), err2[0].cpu().numpy())
+    if apply:
+        return out[0].cpu().numpy(), wxy, errs
+    return wxy, errs

@@ -1,0 +1,100 @@
+"""Install the CUDA path underneath an importable QAMpy so that ``qampy.equalisation.equalise_signal /
+dual_mode_equalisation / apply_filter`` and ``qampy.phaserec.bps`` (and the scripts built on them) run
+unchanged.
+
+Two seams:
+
+* ``level="l2"`` (default, fast): replace the L2 drivers ``qampy.core.equalisation.{equalise_signal,
+  dual_mode_equalisation, apply_filter}`` and ``qampy.core.phaserecovery.bps`` -- the signal stays in
+  HBM across train -> train -> apply.
+* ``level="l1"``: replace only the Pythran kernels the L2 code calls (``pythran_equalisation.
+  train_equaliser / apply_filter_to_signal`` by module attribute, ``phaserecovery._bps_idx_pyt /
+  select_angles`` which were from-imported at import time).  This is the parity-test seam.
+
+Real-valued methods (``*_real``) are left on the reference path.
+"""
+import contextlib
+import importlib
+
+_saved = []
+
+
+def _set(obj, name, new):
+    _saved.append((obj, name, getattr(obj, name)))
+    setattr(obj, name, new)
+
+
+def patch(level="l2"):
+    """Patch an importable ``qampy``.  Returns the list of patched attribute names."""
+    if _saved:
+        unpatch()
+    from . import equalisation as q_eq, phaserecovery as q_ph, pythran_dsp as q_dsp, pythran_equalisation as q_pe
+    from .theory import REAL_VALUED
+    ceq_pkg = importlib.import_module("qampy.core.equalisation")
+    ceq = importlib.import_module("qampy.core.equalisation.equalisation")
+    cph = importlib.import_module("qampy.core.phaserecovery")
+    ref_pe = importlib.import_module("qampy.core.equalisation.pythran_equalisation")
+    if level == "l1":
+        _set(ref_pe, "train_equaliser", q_pe.train_equaliser)
+        ref_apply = ref_pe.apply_filter_to_signal
+
+        def apply_filter_to_signal(E, os, wx, modes=None):
+            import numpy as np
+            if np.iscomplexobj(E) and np.iscomplexobj(wx):
+                return q_pe.apply_filter_to_signal(E, os, wx, modes)
+            return ref_apply(E, os, wx, modes)          # real-valued taps: reference path
+
+        _set(ref_pe, "apply_filter_to_signal", apply_filter_to_signal)
+        _set(cph, "_bps_idx_pyt", q_dsp.bps)
+        _set(cph, "select_angles", q_dsp.select_angles)
+    elif level == "l2":
+        ref = {n: getattr(ceq, n) for n in ("equalise_signal", "dual_mode_equalisation", "apply_filter")}
+
+        def equalise_signal(E, os, mu, M, *args, **kwargs):
+            method = kwargs.get("method", args[4] if len(args) > 4 else "mcma")
+            if str(method).lower() in REAL_VALUED:
+                return ref["equalise_signal"](E, os, mu, M, *args, **kwargs)
+            return q_eq.equalise_signal(E, os, mu, M, *args, **kwargs)
+
+        def dual_mode_equalisation(E, os, mu, M, *args, **kwargs):
+            methods = kwargs.get("methods", args[4] if len(args) > 4 else ("mcma", "sbd"))
+            if any(str(m).lower() in REAL_VALUED for m in methods):
+                return ref["dual_mode_equalisation"](E, os, mu, M, *args, **kwargs)
+            return q_eq.dual_mode_equalisation(E, os, mu, M, *args, **kwargs)
+
+        def apply_filter(E, os, wxy, method="pyt", modes=None):
+            import numpy as np
+            if method != "pyt" or not (np.iscomplexobj(E) and np.iscomplexobj(wxy)):
+                return ref["apply_filter"](E, os, wxy, method=method, modes=modes)
+            return q_eq.apply_filter(E, os, wxy, method=method, modes=modes)
+
+        for mod in (ceq, ceq_pkg):
+            _set(mod, "equalise_signal", equalise_signal)
+            _set(mod, "dual_mode_equalisation", dual_mode_equalisation)
+            _set(mod, "apply_filter", apply_filter)
+        ref_bps = cph.bps
+
+        def bps(E, Mtestangles, symbols, N, method="pyt", **kwargs):
+            if method.lower() != "pyt":
+                return ref_bps(E, Mtestangles, symbols, N, method=method, **kwargs)
+            return q_ph.bps(E, Mtestangles, symbols, N, method=method, **kwargs)
+
+        _set(cph, "bps", bps)
+    else:
+        raise ValueError("level must be 'l1' or 'l2'")
+    return [name for _, name, _ in _saved]
+
+
+def unpatch():
+    while _saved:
+        obj, name, old = _saved.pop()
+        setattr(obj, name, old)
+
+
+@contextlib.contextmanager
+def patched(level="l2"):
+    patch(level)
+    try:
+        yield
+    finally:
+        unpatch()

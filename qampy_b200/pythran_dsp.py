@@ -1,0 +1,53 @@
+"""Drop-in for the reference's L1 blind-phase-search kernels (``qampy/core/pythran_dsp.py``):
+
+* ``bps(E, testangles, symbols, N)`` -> int32 angle indices   (:45-85 incl. select_angle_index :26-42)
+* ``select_angles(angles, idx)``                              (:133-153)
+
+NumPy in / NumPy out through the C ABI's ``*_host`` entry points (CUDA only, no CPU path).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .pythran_equalisation import _ctype, _p
+
+
+def _rtype(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return _lib.QB_C64, np.float32
+    if dtype == np.float64:
+        return _lib.QB_C128, np.float64
+    raise TypeError("angles must be float32 or float64, got %s" % dtype)
+
+
+def bps(E, testangles, symbols, N):
+    """Blind phase search index search for one 1-D signal.  ``testangles`` is (1, A); the
+    per-symbol table form (L, A) used by two-stage BPS is not implemented in CUDA."""
+    code, rt, ct = _ctype(np.asarray(E).dtype)
+    E = np.ascontiguousarray(E, dtype=ct)
+    if E.ndim != 1:
+        raise ValueError("E must be 1-dimensional")
+    testangles = np.atleast_2d(np.asarray(testangles, dtype=rt))
+    if testangles.shape[0] != 1:
+        raise NotImplementedError("per-symbol test-angle tables (two-stage BPS) are not implemented in CUDA")
+    comp = np.ascontiguousarray(np.exp(1j * testangles)[0], dtype=ct)   # pythran_dsp.py:72
+    symbols = np.ascontiguousarray(symbols, dtype=ct).reshape(-1)
+    idx = np.zeros(E.shape[0], dtype=np.int32)
+    _lib.check(_lib.load().qb_bps_host(code, _p(E), 1, E.shape[0], _p(comp), None, comp.size, _p(symbols),
+                                       symbols.size, int(N), _p(idx), None, None))
+    return idx
+
+
+def select_angles(angles, idx):
+    angles = np.atleast_2d(np.asarray(angles))
+    code, rt = _rtype(angles.dtype)
+    angles = np.ascontiguousarray(angles, dtype=rt)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    p, A = angles.shape
+    L = p if p > 1 else idx.shape[0]
+    assert idx.shape[0] >= L
+    out = np.zeros(L, dtype=rt)
+    _lib.check(_lib.load().qb_select_angles_host(code, _p(angles), p, A, _p(idx), L, _p(out)))
+    return out

@@ -1,0 +1,98 @@
+"""Drop-in for the reference's L1 equaliser kernels (NumPy arrays in, NumPy arrays out).
+
+Mirrors the call signatures of ``qampy/core/equalisation/pythran_equalisation.py``:
+
+* ``train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, method)``  (:128-173)
+* ``apply_filter_to_signal(E, os, wx, modes=None)``                                    (:33-76)
+
+Both go through the C ABI's ``*_host`` entry points, i.e. hand-written CUDA on the current device;
+there is no CPU path.  Where compiled Pythran would raise ``TypeError`` for a dtype combination
+outside its export list (E / wx / symbols of different width, Python-int modes) this shim casts.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _ctype(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.complex64:
+        return _lib.QB_C64, np.float32, np.complex64
+    if dtype == np.complex128:
+        return _lib.QB_C128, np.float64, np.complex128
+    if dtype in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise NotImplementedError("real-valued signals/taps are not part of the CUDA hot path")
+    raise TypeError("E must be complex64 or complex128, got %s" % dtype)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, method, mu_shared=True):
+    """Train the equaliser taps.  ``wx`` is updated in place and returned, like the reference
+    (:170, :173).  Returns ``(err, wx, mu)``.
+
+    ``mu_shared`` only matters for ``adaptive=True`` with more than one mode: True carries one step
+    size through the modes in list order (what the reference does when interpreted, :130/:162-172),
+    False starts every mode from ``mu``.
+    """
+    if method not in _lib.METHODS:
+        raise ValueError("Unknown method %s" % method)
+    code, rt, ct = _ctype(np.asarray(E).dtype)
+    E = np.ascontiguousarray(E, dtype=ct)
+    if E.ndim != 2:
+        raise ValueError("E must be 2-dimensional (modes, samples)")
+    wx_in = wx
+    wx_c = np.ascontiguousarray(wx, dtype=ct)
+    if wx_c.ndim != 3:
+        raise ValueError("wx needs to be three dimensional")
+    nmodes, L = E.shape
+    ntaps = wx_c.shape[-1]
+    assert wx_c.shape[0] == nmodes and wx_c.shape[1] == nmodes, \
+        "wx needs to have at least as many dimensions as the maximum mode"
+    symbols = np.ascontiguousarray(symbols, dtype=ct)
+    assert symbols.ndim == 2 and symbols.shape[0] == nmodes, "symbols must be at least size of modes"
+    modes = np.ascontiguousarray(np.atleast_1d(modes), dtype=np.int64)
+    TrSyms, Niter, os = int(TrSyms), int(Niter), int(os)
+    err = np.zeros((nmodes, TrSyms * Niter), dtype=ct)
+    mu_io = np.array([mu], dtype=rt)
+    _lib.check(_lib.load().qb_train_equaliser_host(
+        code, _p(E), nmodes, L, TrSyms, Niter, os, _p(mu_io), _p(wx_c), ntaps, _p(modes), modes.size,
+        int(bool(adaptive)), _p(symbols), symbols.shape[1], _lib.METHODS[method], int(bool(mu_shared)), _p(err)))
+    if wx_c is not wx_in:
+        if isinstance(wx_in, np.ndarray) and wx_in.dtype == ct:
+            np.copyto(wx_in, wx_c)     # keep the in-place contract for non-contiguous views
+            wx_c = wx_in
+    return err, wx_c, mu_io[0]
+
+
+def apply_filter_to_signal(E, os, wx, modes=None):
+    """Static MIMO FIR + decimation: returns (len(modes), (L - ntaps + 1)//os)."""
+    assert os > 0, "oversampling factor must be larger than 0"
+    code, rt, ct = _ctype(np.asarray(E).dtype)
+    if not np.iscomplexobj(wx):
+        raise NotImplementedError("real-valued taps are not part of the CUDA hot path")
+    E = np.ascontiguousarray(E, dtype=ct)
+    wx = np.ascontiguousarray(wx, dtype=ct)
+    nmodes_max = wx.shape[0]
+    ntaps = wx.shape[-1]
+    if modes is None:
+        modes = np.arange(nmodes_max)
+    else:
+        modes = np.atleast_1d(modes)
+        assert np.max(modes) < nmodes_max, "largest mode number is larger than shape of signal"
+    modes = np.ascontiguousarray(modes, dtype=np.int64)
+    nmodes, L = E.shape
+    N = max((L - ntaps + 1) // int(os), 0)
+    out = np.zeros((modes.size, N), dtype=ct)
+    _lib.check(_lib.load().qb_apply_filter_to_signal_host(code, _p(E), nmodes, L, int(os), _p(wx), ntaps,
+                                                         _p(modes), modes.size, _p(out)))
+    return out
+
+
+def train_equaliser_realvalued(*args, **kwargs):
+    raise NotImplementedError("train_equaliser_realvalued (4x4 real MIMO) is outside the CUDA hot path "
+                              "(SURVEY.md section 8f-4)")

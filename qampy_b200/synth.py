@@ -1,0 +1,113 @@
+"""Synthetic impaired coherent-receiver input for tests and bench.py (``"data": "synthetic"``).
+
+Not on the hot path: plain torch ops, runs on CPU or on the GPU.  The recipe mirrors what the
+reference's generators do for the BASELINE configs: Gray-agnostic random M-QAM
+symbols at unit power -> root-raised-cosine pulse shaping to ``os`` samples per symbol
+(``qampy/core/resample.py:73-126``) -> AWGN at a per-symbol SNR (``core/impairments.py:210-233``:
+noise std = sqrt(P * os) * 10^(-snr/20)) -> first-order PMD in the frequency domain
+(``core/impairments.py:94-131``) -> optional Wiener phase noise (``:133-186``).  The reference's own
+generators are used for the golden fixtures (``tests/golden``); this one exists because the GPU box
+has no reference checkout and config C3/C5 inputs are too large to synthesise on the host.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .theory import normalised_symbols
+
+
+def _rrc_freq(n, os, beta, device):
+    """|H(f)| of a root-raised-cosine with symbol rate 1 and sampling rate ``os`` on an n-point FFT grid."""
+    f = torch.fft.fftfreq(n, d=1.0 / os, device=device, dtype=torch.float64).abs()
+    H = torch.zeros(n, dtype=torch.float64, device=device)
+    lo, hi = (1 - beta) / 2, (1 + beta) / 2
+    H[f <= lo] = 1.0
+    if beta > 0:
+        band = (f > lo) & (f <= hi)
+        H[band] = torch.sqrt(0.5 * (1 + torch.cos(math.pi / beta * (f[band] - lo))))
+    return H
+
+
+def synth_signal(M, nsym, nmodes=2, os=2, beta=0.1, snr_db=28.0, theta=math.pi / 5.6, dgd=40e-12, fb=40e9,
+                 linewidth=None, seed=0, dtype=torch.complex64, device="cpu"):
+    """Returns ``(E, symbols)``: E (nmodes, nsym*os) impaired signal, symbols (nmodes, nsym) sent."""
+    device = torch.device(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    alphabet = torch.from_numpy(normalised_symbols(M)).to(device)
+    idx = torch.randint(0, M, (nmodes, nsym), generator=gen, device=device)
+    syms = alphabet[idx]
+    n = nsym * os
+    x = torch.zeros((nmodes, n), dtype=torch.complex128, device=device)
+    x[:, ::os] = syms
+    X = torch.fft.fft(x, dim=1) * _rrc_freq(n, os, beta, device)
+    if nmodes == 2 and theta is not None:
+        # first-order PMD: rotate, delay the axes by +-dgd/2, rotate back
+        omega = 2 * math.pi * torch.fft.fftfreq(n, d=1.0 / (os * fb), device=device, dtype=torch.float64)
+        c, s = math.cos(theta), math.sin(theta)
+        a = c * X[0] + s * X[1]
+        b = -s * X[0] + c * X[1]
+        a = a * torch.exp(-0.5j * omega * dgd)
+        b = b * torch.exp(0.5j * omega * dgd)
+        X = torch.stack([c * a - s * b, s * a + c * b])
+    x = torch.fft.ifft(X, dim=1)
+    x = x / torch.sqrt((x.abs() ** 2).mean(dim=1, keepdim=True))
+    if snr_db is not None:
+        sigma = math.sqrt(os) * 10 ** (-snr_db / 20)
+        noise = torch.randn((nmodes, n, 2), generator=gen, device=device, dtype=torch.float64)
+        x = x + sigma / math.sqrt(2) * torch.view_as_complex(noise)
+    if linewidth:
+        x = apply_phase_noise(x, linewidth, os * fb, seed=seed + 1)
+    return x.to(dtype), syms.to(dtype)
+
+
+def apply_phase_noise(x, linewidth, fs, seed=0):
+    """Wiener phase walk with variance 2*pi*linewidth/fs per sample, independent per row."""
+    gen = torch.Generator(device=x.device)
+    gen.manual_seed(int(seed))
+    var = 2 * math.pi * linewidth / fs
+    steps = torch.randn(x.shape, generator=gen, device=x.device, dtype=torch.float64) * math.sqrt(var)
+    ph = torch.cumsum(steps, dim=-1)
+    return (x.to(torch.complex128) * torch.exp(1j * ph)).to(x.dtype)
+
+
+def synth_numpy(*args, **kwargs):
+    E, s = synth_signal(*args, **kwargs)
+    return E.cpu().numpy(), s.cpu().numpy()
+
+
+def decide(E, M):
+    """Nearest-symbol decisions (host, NumPy) on the unit-power M-QAM alphabet."""
+    alphabet = normalised_symbols(M).astype(np.complex64)
+    E = np.asarray(E)
+    out = np.empty(E.shape, dtype=np.complex64)
+    flat, oflat = E.reshape(-1), out.reshape(-1)
+    for a in range(0, flat.size, 65536):
+        c = flat[a:a + 65536]
+        oflat[a:a + 65536] = alphabet[np.argmin(np.abs(c[:, None] - alphabet[None, :]), axis=1)]
+    return out
+
+
+def ser(E, syms, M, max_delay=64, probe=2000):
+    """Symbol error rate of equalised 1-sps ``E`` against the sent ``syms``, after resolving what a
+    blind receiver leaves open: which sent row each output row carries, a multiple-of-pi/2 rotation
+    and an integer symbol delay (found on the first ``probe`` symbols, then applied to all)."""
+    dec = decide(E, M)
+    syms = np.asarray(syms)
+    total = []
+    for r in range(dec.shape[0]):
+        best = (2.0, 0, 0, 0)
+        n = min(probe, dec.shape[1] - max_delay)
+        for src in range(syms.shape[0]):
+            for rot in range(4):
+                ref = syms[src] * (1j ** rot)
+                for d in range(0, max_delay):
+                    e = float(np.mean(np.abs(dec[r, :n] - ref[d:d + n]) > 1e-3))
+                    if e < best[0]:
+                        best = (e, src, rot, d)
+        _, src, rot, d = best
+        ref = syms[src] * (1j ** rot)
+        m = min(dec.shape[1], ref.size - d)
+        total.append(float(np.mean(np.abs(dec[r, :m] - ref[d:d + m]) > 1e-3)))
+    return float(np.mean(total))
