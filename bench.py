@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the qampy_b200 hot path (BASELINE.json metric).
+
+Workload (``config.workload``): BASELINE config C3 per GPU -- dual-pol 64-QAM, 2 samples/symbol,
+``--nsym`` (default 1e7) symbols, MCMA -> MRDE training (ntaps 45, mu 1e-3) -> apply -> BPS(64 test
+angles, N = 45), processed as independent time segments of ``--seg`` output symbols (ntaps-1 overlap,
+every segment trained from centre-spike taps; segment s == the reference called on that segment).
+One "step" = one pass of the whole chain over the capture.  N > 1: every rank owns its own capture
+(weak scaling, no collective on the data path); the reported value is the sum over ranks divided by
+the max-over-ranks device time.
+
+    python bench.py [--gpus N --steps K --warmup W]           # this project's CUDA path
+    python bench.py --impl reference [...]                     # reference-equivalent CPU path (oracle port)
+
+Prints ONE JSON line (see the task contract): value = Msamples/s with inputs resident in HBM,
+e2e = same metric from pinned host buffers through H2D / D2H, roofline for the dominant kernel
+(train), cpu_baseline = the oracle (reference's compile flags) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Msamples/s dual-pol 64-QAM MCMA->MRDE->BPS"
+# algorithmic bytes per symbol period (dual-pol, os=2, complex64), SURVEY.md section 8d / DESIGN.md
+BYTES_TRAIN, BYTES_APPLY, BYTES_BPS = 48, 48, 40
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nsym", type=int, default=10 ** 7, help="symbols per polarisation per GPU")
+    ap.add_argument("--seg", type=int, default=8192, help="output symbols per segment (0 = one segment)")
+    ap.add_argument("--ntaps", type=int, default=45)
+    ap.add_argument("--M", type=int, default=64)
+    ap.add_argument("--angles", type=int, default=64)
+    ap.add_argument("--bpsN", type=int, default=45)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {"workload": "C3 dual-pol %d-QAM dual_mode_equalisation(mcma->mrde, ntaps=%d, mu=1e-3) + bps(%d, N=%d), "
+                        "2 sps, %d symbols per GPU" % (a.M, a.ntaps, a.angles, a.bpsN, a.nsym),
+            "symbols_per_gpu": a.nsym, "samples_per_gpu": 2 * a.nsym, "segment_symbols": a.seg or a.nsym,
+            "segment_semantics": "each segment == reference call on that segment (centre-spike taps)",
+            "sharding": "dp%d (independent captures per rank, no collective)" % world,
+            "l2_policy": "inputs (320 MB/GPU) larger than L2 (126 MB); no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port compiled with the reference's flags, on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_chain(a, nseg, seed=1234):
+    """Times the reference-equivalent CPU chain on `nseg` segments of the workload.  Returns
+    (seconds, samples processed, threads)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_oracle as co
+    from qampy_b200 import synth, theory
+    S = a.seg or a.nsym
+    nsym = nseg * S + (a.ntaps - 1 + 1) // 2
+    E, _ = synth.synth_numpy(a.M, nsym, seed=seed, snr_db=28.0)
+    L_seg = S * 2 + a.ntaps - 1
+    Es = np.stack([E[:, s * S * 2: s * S * 2 + L_seg] for s in range(nseg)])   # (nseg, 2, L_seg)
+    kind = "fast_native"
+    lib = co.lib(kind)
+    threads = lib.qo_max_threads()
+    alphabet = theory.normalised_symbols(a.M).astype(np.complex64)
+    ang = theory.bps_test_angles(a.angles, np.float32)
+    w = np.tile(theory.init_taps(a.ntaps, 2, np.complex64), (nseg, 1, 1, 1))
+    tr = theory.cal_training_symbol_len(2, a.ntaps, L_seg)
+    s1 = theory.reshape_symbols(None, "mcma", a.M, np.complex64, 2)
+    s2 = theory.reshape_symbols(None, "mrde", a.M, np.complex64, 2)
+    t0 = time.perf_counter()
+    co.train_segments(Es, tr, 1, 2, 1e-3, w, [0, 1], False, s1, "mcma", mu_shared=False, kind=kind)
+    co.train_segments(Es, tr, 1, 2, 1e-3, w, [0, 1], False, s2, "mrde", mu_shared=False, kind=kind)
+    eq = co.apply_segments(Es, 2, w, None, kind=kind)                           # (nseg, 2, S)
+    idx = co.bps_streams(eq.reshape(nseg * 2, -1), ang, alphabet, a.bpsN, kind=kind)
+    ph = ang[0][idx]
+    ph[:, a.bpsN:-a.bpsN] = np.unwrap(ph[:, a.bpsN:-a.bpsN] * 4) / 4
+    out = eq.reshape(nseg * 2, -1) * np.exp(1j * ph)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(out).all()
+    return dt, nseg * S * 2, threads
+
+
+def cpu_baseline(a, target_s):
+    S = a.seg or a.nsym
+    max_seg = max(1, a.nsym // S)
+    n0 = min(max_seg, 16)
+    dt, samples, threads = cpu_chain(a, n0)
+    nseg = int(min(max_seg, max(n0, n0 * target_s / max(dt, 1e-3))))
+    if nseg > n0:
+        dt, samples, threads = cpu_chain(a, nseg)
+    else:
+        nseg = n0
+    return {"value": samples / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d segments of %d symbols (%.1f s of CPU work; oracle C port built with the "
+                      "reference's flags -O3 -ffast-math -march=native -fopenmp; Pythran itself is not "
+                      "installable here)" % (nseg, max_seg, S, dt)}, dt
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    S = a.seg or a.nsym
+    # calibrate the per-step sample so that warmup+steps stay within a few minutes
+    base, t0 = cpu_baseline(a, min(a.cpu_seconds, 6.0))
+    nseg = int(base["sample"].split(" of ")[0])
+    times = []
+    for i in range(a.warmup + a.steps):
+        dt, samples, threads = cpu_chain(a, nseg, seed=100 + i)
+        if i >= a.warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    val = samples / t / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, world),
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                             "sample": "each step: %d segments of %d symbols of the workload" % (nseg, S)},
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(a, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from qampy_b200 import _lib, pipeline, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = pipeline.ReceiverConfig(M=a.M, ntaps=a.ntaps, os=2, mu=(1e-3, 1e-3), methods=("mcma", "mrde"),
+                                  bps_angles=a.angles, bps_N=a.bpsN, seg_symbols=a.seg or None)
+    rx = pipeline.SegmentedReceiver(cfg, dev)
+    rx.want_idx = False
+    E, syms = synth.synth_signal(a.M, a.nsym, seed=1000 + rank, snr_db=28.0, device=dev)
+    L = E.shape[1]
+    groups = pipeline.plan_segments(L, cfg)
+    nsym_out = sum(n * k for _, n, k, _ in groups)
+    torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        res = rx.run(E)
+    # sanity gate (printed with the number): equaliser output power and SER of one segment
+    eq0 = res[0]["eq"][0].cpu().numpy()
+    S0 = res[0]["nsym"]
+    out_rms = float(np.sqrt(np.mean(np.abs(eq0) ** 2)))
+    ser = synth.ser(eq0[:, :min(S0, 20000)], syms[:, :min(S0, 20000) + 200].cpu().numpy(), a.M)
+    del res
+
+    launches0 = _lib.launch_count()
+    rx.events = []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        res = rx.run(E)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    events, rx.events = rx.events, None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / a.steps
+    value = world * L / (ms_step * 1e-3) / 1e6
+
+    # per-kernel device time inside the timed region (events on the launching stream)
+    per = {}
+    for name, (s, e) in events:
+        per.setdefault(name, []).append(s.elapsed_time(e))
+    # dominant kernel: eq_train.  One step launches it once per stage and segment group.
+    train_ms = sum(per.get("train", [0.0])) / a.steps
+    train_bytes = BYTES_TRAIN * nsym_out * len(cfg.methods)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = train_bytes / (train_ms * 1e-3) / 1e9 if train_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "train_warp_kernel<float,3> (both stages)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "binding_limit": "serial recurrence latency / FP32 issue, not HBM (DESIGN.md)",
+                "stage_ms_per_step": {k: sum(v) / a.steps for k, v in per.items()},
+                "stage_gbs": {"train": achieved,
+                              "apply": BYTES_APPLY * nsym_out / (sum(per.get("apply", [0])) / a.steps * 1e-3) / 1e9
+                              if per.get("apply") else None,
+                              "bps": BYTES_BPS * nsym_out / (sum(per.get("bps", [0])) / a.steps * 1e-3) / 1e9
+                              if per.get("bps") else None}}
+
+    # end to end: pinned host input -> H2D -> chain -> D2H of the recovered symbols + phase
+    e2e = None
+    if not a.no_e2e:
+        Eh = torch.empty(E.shape, dtype=E.dtype, pin_memory=True)
+        Eh.copy_(E)
+        Ed = torch.empty_like(E)
+        outs_h = None
+        times = []
+        for it in range(2 + a.steps):
+            barrier()
+            t0 = time.perf_counter()
+            Ed.copy_(Eh, non_blocking=True)
+            res = rx.run(Ed)
+            if outs_h is None:
+                outs_h = [(torch.empty(g["out"].shape, dtype=g["out"].dtype, pin_memory=True),
+                           torch.empty(g["ph"].shape, dtype=g["ph"].dtype, pin_memory=True)) for g in res]
+            for g, (oh, ph) in zip(res, outs_h):
+                oh.copy_(g["out"], non_blocking=True)
+                ph.copy_(g["ph"], non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it >= 2:
+                times.append(dt)
+        t = sum(times) / len(times)
+        if world > 1:
+            tt = torch.tensor([t], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        h2d = E.numel() * E.element_size()
+        d2h = sum(o.numel() * o.element_size() + p.numel() * p.element_size() for o, p in outs_h)
+        e2e = {"value": world * L / t / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": t * 1e3,
+               "api": "pinned host capture -> qampy_b200.pipeline.SegmentedReceiver.run -> pinned host symbols+phase"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "msymbols_per_s": value / 2, "sanity": {"eq_out_rms": out_rms, "ser_segment0": ser}}
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                line["cpu_baseline"], _ = cpu_baseline(a, a.cpu_seconds)
+            except Exception as exc:   # the GPU number stands on its own
+                line["cpu_baseline"] = {"value": None, "error": repr(exc)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_b200(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,17 +38,17 @@ struct BpsParams {
     int tile_rows, ring_rows;
 };
 
+// Per-axis slicer.  `pairs[f] = (lev[f], lev[f+1])` are the two levels bracketing a value whose
+// (approximate) grid coordinate floors to f; the nearest level is always one of them, and because the
+// subtraction uses the STORED level values the result is bit-identical to the brute-force minimum.
 template <typename T>
-__device__ __forceinline__ T axis_min(T t, const T *lev, int n, T lev0, T inv_step)
+__device__ __forceinline__ T axis_min(T t, const cx<T> *pairs, int npair, T lev0, T inv_step)
 {
-    // nearest level is within +-1 of the rounded guess; evaluate all three (clamped)
-    T gf = rint((t - lev0) * inv_step);
-    gf = gf > (T)0 ? gf : (T)0;  // NaN -> 0
-    gf = gf < (T)(n - 1) ? gf : (T)(n - 1);
-    const int g = (int)gf;
-    const int g0 = g > 0 ? g - 1 : 0, g2 = g < n - 1 ? g + 1 : n - 1;
-    const T d0 = fabs(sub_rn(t, lev[g0])), d1 = fabs(sub_rn(t, lev[g])), d2 = fabs(sub_rn(t, lev[g2]));
-    return fmin(fmin(d0, d1), d2);  // NaN only if t is NaN
+    T uf = floor((t - lev0) * inv_step);
+    uf = uf > (T)0 ? uf : (T)0;  // NaN -> 0
+    uf = uf < (T)(npair - 1) ? uf : (T)(npair - 1);
+    const cx<T> l = pairs[(int)uf];
+    return fmin(fabs(sub_rn(t, l.x)), fabs(sub_rn(t, l.y)));  // NaN only if t is NaN
 }
 
 template <typename T>
@@ -96,17 +96,19 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int A = p.A, W = 2 * p.N, N = p.N, TR = p.tile_rows, RR = p.ring_rows;
+    const int A = p.A, W = 2 * p.N, N = p.N, TR = p.tile_rows;
+    const int RMASK = p.ring_rows - 1;  // ring_rows is a power of two >= TR + W
     const long long L = p.L;
 
     cx<T> *comp = reinterpret_cast<cx<T> *>(smem_raw);  // [A]
-    cx<T> *syms = comp + A;                             // [M] (brute force only)
-    T *ring = reinterpret_cast<T *>(syms + (p.n_re ? 0 : p.M));  // [RR][A] running sums (x before phase 2)
-    T *dt = ring + (size_t)RR * A;                      // [TR][A] window differences
+    cx<T> *syms = comp + A;                             // [M] (brute force) or level pairs (slicer)
+    const bool slicer = p.n_re > 0;
+    const int npr = slicer ? max(p.n_re - 1, 1) : 0, npi = slicer ? max(p.n_im - 1, 1) : 0;
+    cx<T> *pre = syms, *pim = syms + npr;
+    T *ring = reinterpret_cast<T *>(syms + (slicer ? npr + npi : p.M));  // [RR][A] running sums
+    T *dt = ring + (size_t)p.ring_rows * A;             // [TR][A] window differences
     T *angs = dt + (size_t)TR * A;                      // [A]
-    T *lre = angs + A;                                  // [n_re]
-    T *lim = lre + p.n_re;                              // [n_im]
-    T *p4s = lim + p.n_im;                              // [TR] 4*angle of the tile's output rows
+    T *p4s = angs + A;                                  // [TR] 4*angle of the tile's output rows
     int *kidx = reinterpret_cast<int *>(p4s + TR);      // [TR]
 
     const cx<T> *E = p.E + (long long)blockIdx.x * p.stream_stride;
@@ -118,21 +120,20 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
         comp[c] = p.comp[c];
         angs[c] = p.angles ? p.angles[c] : (T)0;
     }
-    const bool slicer = p.n_re > 0;
+    T re0 = 0, rinv = 0, im0 = 0, iinv = 0;
     if (slicer) {
-        for (int c = tid; c < p.n_re; c += BPS_THREADS) lre[c] = p.lev_re[c];
-        for (int c = tid; c < p.n_im; c += BPS_THREADS) lim[c] = p.lev_im[c];
+        for (int c = tid; c < npr; c += BPS_THREADS)
+            pre[c] = make_cx<T>(p.lev_re[c], p.lev_re[min(c + 1, p.n_re - 1)]);
+        for (int c = tid; c < npi; c += BPS_THREADS)
+            pim[c] = make_cx<T>(p.lev_im[c], p.lev_im[min(c + 1, p.n_im - 1)]);
+        re0 = p.lev_re[0];
+        im0 = p.lev_im[0];
+        rinv = p.n_re > 1 ? (T)(p.n_re - 1) / (p.lev_re[p.n_re - 1] - re0) : (T)0;
+        iinv = p.n_im > 1 ? (T)(p.n_im - 1) / (p.lev_im[p.n_im - 1] - im0) : (T)0;
     } else {
         for (int c = tid; c < p.M; c += BPS_THREADS) syms[c] = p.symbols[c];
     }
     __syncthreads();
-    T re0 = 0, rinv = 0, im0 = 0, iinv = 0;
-    if (slicer) {
-        re0 = lre[0];
-        im0 = lim[0];
-        rinv = p.n_re > 1 ? (T)(p.n_re - 1) / (lre[p.n_re - 1] - re0) : (T)0;
-        iinv = p.n_im > 1 ? (T)(p.n_im - 1) / (lim[p.n_im - 1] - im0) : (T)0;
-    }
 
     // edges: idx = 0 -> ph = angles[0], not unwrapped (phaserecovery.py:155 touches [N:-N] only)
     const long long lo = N < L ? N : L;                  // rows [0, lo) are left edge
@@ -148,53 +149,84 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
         }
     }
 
+    // phase-1 mapping: when A divides the block, a thread keeps one angle (its rotation in registers)
+    const bool fixed = (BPS_THREADS % A) == 0;
+    const int my_a = tid % A, my_r0 = tid / A, rstep = fixed ? BPS_THREADS / A : 1;
+    const cx<T> my_c = comp[my_a];
+
     T csum = 0;                 // running column sum, owned by thread a < A
     T cum = 0, p4prev = 0;      // unwrap state, replicated in warp 0
+    int slot0 = 0;              // ring slot of the tile's first row
 
-    for (long long i0 = 0; i0 < L; i0 += TR) {
+    for (long long i0 = 0; i0 < L; i0 += TR, slot0 = (slot0 + TR) & RMASK) {
         const int nrows = (int)min((long long)TR, L - i0);
         // ---- phase 1: distances of the tile into the ring ---------------------------------------
-        for (int f = tid; f < nrows * A; f += BPS_THREADS) {
-            const int r = f / A, a = f - r * A;
-            const cx<T> e = E[i0 + r];
-            const cx<T> c = comp[a];
-            const T tr = sub_rn(mul_rn(e.x, c.x), mul_rn(e.y, c.y));
-            const T ti = add_rn(mul_rn(e.x, c.y), mul_rn(e.y, c.x));
-            T d;
-            if (slicer) {
-                const T da = axis_min<T>(tr, lre, p.n_re, re0, rinv);
-                const T db = axis_min<T>(ti, lim, p.n_im, im0, iinv);
-                d = add_rn(mul_rn(da, da), mul_rn(db, db));
-            } else {
-                d = (T)1000.;
-                for (int m = 0; m < p.M; m++) {
-                    const cx<T> sy = syms[m];
-                    const T dr = sub_rn(tr, sy.x), di = sub_rn(ti, sy.y);
-                    const T dd = add_rn(mul_rn(dr, dr), mul_rn(di, di));
-                    if (dd < d) d = dd;
+        if (fixed) {
+            for (int r = my_r0; r < nrows; r += rstep) {
+                const cx<T> e = E[i0 + r];
+                const T tr = sub_rn(mul_rn(e.x, my_c.x), mul_rn(e.y, my_c.y));
+                const T ti = add_rn(mul_rn(e.x, my_c.y), mul_rn(e.y, my_c.x));
+                T d;
+                if (slicer) {
+                    const T da = axis_min<T>(tr, pre, npr, re0, rinv);
+                    const T db = axis_min<T>(ti, pim, npi, im0, iinv);
+                    d = add_rn(mul_rn(da, da), mul_rn(db, db));
+                } else {
+                    d = (T)1000.;
+                    for (int m = 0; m < p.M; m++) {
+                        const cx<T> sy = syms[m];
+                        const T dr = sub_rn(tr, sy.x), di = sub_rn(ti, sy.y);
+                        const T dd = add_rn(mul_rn(dr, dr), mul_rn(di, di));
+                        if (dd < d) d = dd;
+                    }
                 }
+                ring[((slot0 + r) & RMASK) * A + my_a] = d < (T)100. ? d : (T)100.;
             }
-            ring[(size_t)((i0 + r) % RR) * A + a] = d < (T)100. ? d : (T)100.;
+        } else {
+            for (int f = tid; f < nrows * A; f += BPS_THREADS) {
+                const int r = f / A, a = f - r * A;
+                const cx<T> e = E[i0 + r];
+                const cx<T> c = comp[a];
+                const T tr = sub_rn(mul_rn(e.x, c.x), mul_rn(e.y, c.y));
+                const T ti = add_rn(mul_rn(e.x, c.y), mul_rn(e.y, c.x));
+                T d;
+                if (slicer) {
+                    const T da = axis_min<T>(tr, pre, npr, re0, rinv);
+                    const T db = axis_min<T>(ti, pim, npi, im0, iinv);
+                    d = add_rn(mul_rn(da, da), mul_rn(db, db));
+                } else {
+                    d = (T)1000.;
+                    for (int m = 0; m < p.M; m++) {
+                        const cx<T> sy = syms[m];
+                        const T dr = sub_rn(tr, sy.x), di = sub_rn(ti, sy.y);
+                        const T dd = add_rn(mul_rn(dr, dr), mul_rn(di, di));
+                        if (dd < d) d = dd;
+                    }
+                }
+                ring[((slot0 + r) & RMASK) * A + a] = d < (T)100. ? d : (T)100.;
+            }
         }
         __syncthreads();
         // ---- phase 2: sequential running sum per angle column + window difference ---------------
         if (tid < A) {
+            const bool full = i0 >= W && i0 > 0;   // every row of the tile has a complete window
+#pragma unroll 4
             for (int r = 0; r < nrows; r++) {
-                const long long i = i0 + r;
-                T *slot = ring + (size_t)(i % RR) * A + tid;
-                csum = (i == 0) ? (T)0 : add_rn(csum, *slot);   // row 0 is never added (:30)
+                T *slot = ring + ((slot0 + r) & RMASK) * A + tid;
+                const T old = ring[((slot0 + r - W) & RMASK) * A + tid];   // csum[i - W] (garbage if i < W)
+                csum = (i0 + r == 0) ? (T)0 : add_rn(csum, *slot);         // row 0 is never added (:30)
                 *slot = csum;
-                if (i >= W) dt[(size_t)r * A + tid] = sub_rn(csum, ring[(size_t)((i - W) % RR) * A + tid]);
+                if (full || i0 + r >= W) dt[r * A + tid] = sub_rn(csum, old);
             }
         }
         __syncthreads();
         // ---- phase 3: first strict arg-min over angles per row ----------------------------------
-        for (int r = warp; r < nrows; r += BPS_THREADS / 32) {
-            if (i0 + r < W) continue;
+        const int r_first = (int)max((long long)0, (long long)W - i0);
+        for (int r = r_first + warp; r < nrows; r += BPS_THREADS / 32) {
             T best = (T)1000.;
             int bk = 0x7fffffff;
             for (int a = lane; a < A; a += 32) {
-                const T v = dt[(size_t)r * A + a];
+                const T v = dt[r * A + a];
                 if (v < best) {
                     best = v;
                     bk = a;
@@ -217,8 +249,7 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
         }
         __syncthreads();
         // ---- phase 4: np.unwrap(4*ph)/4 over the output rows j = i - N, sequential in fp ----------
-        // rows r with i0 + r >= W produce output j = i0 + r - N; first output overall is j = N.
-        const int r_first = (int)max((long long)0, (long long)W - i0);
+        // rows r >= r_first produce output j = i0 + r - N; the first output overall is j = N.
         if (warp == 0 && ph) {
             for (int rb = r_first; rb < nrows; rb += 32) {
                 const int r = rb + lane;
@@ -238,8 +269,11 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
                     cum = add_rn(cum, ce);
                     if (lane >= e) mycum = cum;
                 }
-                if (valid) ph[j] = add_rn(p4, mycum) / (T)4;
-                // carry the last valid row's 4*angle to the next chunk
+                const T phv = add_rn(p4, mycum) / (T)4;
+                if (valid) {
+                    ph[j] = phv;
+                    p4s[r] = phv;                                // phase 5 reads the final phase from here
+                }
                 const int nvalid = min(32, nrows - rb);
                 p4prev = shfl_idx(p4, nvalid - 1);
             }
@@ -247,15 +281,15 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
         if (idx) {
             for (int r = r_first + tid; r < nrows; r += BPS_THREADS) idx[i0 + r - N] = kidx[r];
         }
-        __syncthreads();
         // ---- phase 5: rotate the tile's output rows ----------------------------------------------
         if (Eout) {
-            __threadfence_block();
+            __syncthreads();
             for (int r = r_first + tid; r < nrows; r += BPS_THREADS) {
                 const long long j = i0 + r - N;
-                Eout[j] = rotate<T>(E[j], ph[j]);
+                Eout[j] = rotate<T>(E[j], p4s[r]);
             }
         }
+        __syncthreads();
     }
 }
 
@@ -284,17 +318,25 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     p.n_im = (int)n_im;
     p.N = (int)N;
     const int W = 2 * (int)N;
-    int TR = 64;
+    // tile rows: fill the power-of-two ring (>= TR + 2N rows) as well as possible, keep <= ~48 KB/CTA
+    // so that several CTAs share an SM and hide each other's serial phases
+    int TR = 0, RR = 0;
     size_t smem = 0;
-    for (; TR >= 8; TR >>= 1) {
-        const size_t RR = (size_t)TR + W;
-        smem = (RR * A + (size_t)TR * A) * sizeof(T) + (A + (n_re ? 0 : M)) * sizeof(cx<T>) +
-               (A + n_re + n_im + TR) * sizeof(T) + TR * sizeof(int) + 64;
-        if (smem <= 200 * 1024) break;
+    for (int rr = 32; rr <= 65536 && !TR; rr <<= 1) {
+        if (rr <= W) continue;
+        int tr = rr - W < 64 ? rr - W : 64;
+        if (tr < 8 && rr < 65536) continue;
+        const size_t need = ((size_t)rr * A + (size_t)tr * A) * sizeof(T) +
+                            (A + (n_re ? n_re + n_im : M)) * sizeof(cx<T>) + (A + tr) * sizeof(T) +
+                            tr * sizeof(int) + 64;
+        if (need > 200 * 1024) break;
+        TR = tr;
+        RR = rr;
+        smem = need;
     }
-    if (TR < 8) return set_error(QB_ERR_UNSUPPORTED, "bps: 2N*A too large for the shared-memory ring");
+    if (!TR) return set_error(QB_ERR_UNSUPPORTED, "bps: 2N*A too large for the shared-memory ring");
     p.tile_rows = TR;
-    p.ring_rows = TR + W;
+    p.ring_rows = RR;
     static bool attr_done[2] = {false, false};
     if (!attr_done[sizeof(T) == 8]) {
         QB_CUDA_CHECK(cudaFuncSetAttribute(bps_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,0 +1,159 @@
+"""Device-resident receiver chain over independent time segments (BASELINE configs C3/C5).
+
+    capture (nmodes, L)  --segment_view-->  (nseg, nmodes, L_seg)      (no copy, ntaps-1 overlap)
+        stage 1 training (e.g. MCMA)        one launch, nseg*nmodes serial streams in parallel
+        stage 2 training (e.g. MRDE)        restarts at sample 0 of the segment with the stage-1 taps
+        apply final taps + decimate         (nseg, nmodes, S) equalised symbols, stays in HBM
+        blind phase search                  (nseg*nmodes) streams of S symbols, fused tail
+
+Semantics (what the parity tests check): segment ``s`` gives exactly what the reference gives when
+``dual_mode_equalisation`` (``qampy/core/equalisation/equalisation.py:400-466``) followed by ``bps``
+(``qampy/core/phaserecovery.py:93-159``) is called on that segment's samples alone, with the taps
+initialised as the caller says (centre spike, or a warm start such as the taps of a previous
+capture -- the reference's own ``wxy=`` mechanism).  Segment ``s`` owns output symbols
+``[s*S, (s+1)*S)`` and reads input samples ``[s*S*os, s*S*os + S*os + ntaps - 1)``; if S does not
+divide the capture, one extra segment of the same length is aligned to the end of the capture.  A single segment (``seg_symbols=None``) is the reference call on the whole
+capture.  Nothing here touches the host between stages and no collective is involved: ranks of a
+multi-GPU job own disjoint ranges of segments (``shard_segments``).
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import device, theory
+
+
+@dataclass
+class ReceiverConfig:
+    M: int = 64
+    ntaps: int = 45
+    os: int = 2
+    mu: tuple = (1e-3, 1e-3)
+    methods: tuple = ("mcma", "mrde")
+    niter: tuple = (1, 1)
+    bps_angles: int = 64
+    bps_N: int = 45
+    seg_symbols: int = None     # output symbols per segment; None = one segment (reference semantics)
+    want_err: bool = False      # keep the per-symbol training error (reference returns it; 16 B/symbol/pass)
+
+
+def plan_segments(L, cfg):
+    """Split the N = (L - ntaps + 1)//os output symbols of a capture into equal segments of
+    cfg.seg_symbols.  Returns a list of groups (first_output_symbol, n_symbols, n_segments, drop):
+    the main group holds the N//S back-to-back segments; if S does not divide N, a second group holds
+    ONE more segment of the same length aligned to the END of the capture (it overlaps its
+    predecessor; only its last N % S symbols -- everything after ``drop`` -- are kept when stitching).
+    All segments therefore have the same length and cost, and the extra one runs concurrently."""
+    N = (L - cfg.ntaps + 1) // cfg.os
+    if N <= 0:
+        raise ValueError("capture shorter than the filter")
+    S = cfg.seg_symbols
+    if S is None or S >= N:
+        return [(0, N, 1, 0)]
+    nfull, rem = divmod(N, S)
+    groups = [(0, S, nfull, 0)]
+    if rem:
+        groups.append((N - S, S, 1, S - rem))
+    return groups
+
+
+def shard_segments(nseg, rank, world):
+    """Contiguous block of segment indices owned by ``rank`` (no exchange between ranks)."""
+    base, extra = divmod(nseg, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class SegmentedReceiver:
+    def __init__(self, cfg, dev=None, cdtype=np.complex64, nmodes=2):
+        self.cfg = cfg
+        self.dev = dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
+        self.cdtype = np.dtype(cdtype)
+        self.tdtype = torch.complex64 if self.cdtype == np.complex64 else torch.complex128
+        self.rdtype = torch.float32 if self.cdtype == np.complex64 else torch.float64
+        self.nmodes = nmodes
+        self.syms = []
+        for m in cfg.methods:
+            if m in theory.DATA_AIDED:
+                raise NotImplementedError("data-aided methods need per-segment training sequences")
+            t = theory.reshape_symbols(None, m, cfg.M, self.cdtype.type, nmodes)
+            self.syms.append(torch.from_numpy(np.ascontiguousarray(t)).to(self.dev))
+        alphabet = theory.normalised_symbols(cfg.M).astype(self.cdtype)
+        self.bps_tables = device.BpsTables(cfg.bps_angles, alphabet, self.cdtype.type, self.dev)
+        self.w0 = torch.from_numpy(theory.init_taps(cfg.ntaps, nmodes, self.cdtype.type)).to(self.dev)
+        self.side = None
+        self.events = None      # set to a list to collect (name, (start, end)) CUDA events per launch
+        self.want_idx = True
+
+    def _tic(self, name):
+        if self.events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            self.events.append((name, ev))
+            return ev[1]
+        return None
+
+    def _run_group(self, E, first, nsym, nseg, drop, wxy0, between):
+        cfg = self.cfg
+        Ev = device.segment_view(E[:, first * cfg.os:], nseg, nsym, cfg.os, cfg.ntaps)
+        L_seg = Ev.shape[2]
+        w0 = self.w0 if wxy0 is None else wxy0          # (nmodes, nmodes, ntaps): same start for all segments
+        assert w0.dim() == 3, "wxy0 must be (nmodes, nmodes, ntaps)"
+        w = w0.expand(nseg, -1, -1, -1).contiguous()
+        trsyms = theory.cal_training_symbol_len(cfg.os, cfg.ntaps, L_seg)
+        errs = []
+        for stage in range(len(cfg.methods)):
+            mu = torch.full((nseg, self.nmodes), float(cfg.mu[stage]), dtype=self.rdtype, device=self.dev)
+            err = None
+            if cfg.want_err:
+                err = torch.empty((nseg, self.nmodes, trsyms * cfg.niter[stage]), dtype=self.tdtype,
+                                  device=self.dev)
+            t = self._tic("train")
+            device.train_equaliser(Ev, trsyms, cfg.niter[stage], cfg.os, mu, w, None, False,
+                                   self.syms[stage], cfg.methods[stage], err)
+            t and t.record()
+            errs.append(err)
+        t = self._tic("apply")
+        eq = device.apply_filter_to_signal(Ev, cfg.os, w)              # (nseg, nmodes, nsym)
+        t and t.record()
+        bin_ = eq if between is None else between(eq)
+        t = self._tic("bps")
+        out, ph, idx = device.bps(bin_.reshape(nseg * self.nmodes, nsym), self.bps_tables, cfg.bps_N,
+                                  want_idx=self.want_idx)
+        t and t.record()
+        if idx is None:
+            idx = ph
+        shp = (nseg, self.nmodes, nsym)
+        return dict(eq=eq, out=out.reshape(shp), ph=ph.reshape(shp), idx=idx.reshape(shp), taps=w, err=errs,
+                    first=first, nsym=nsym, nseg=nseg, drop=drop)
+
+    def run(self, E, wxy0=None, between=None):
+        """E: (nmodes, L) complex CUDA tensor.  Returns one result dict per segment group (see
+        plan_segments); use :func:`stitch` for (nmodes, N) arrays.  The end-aligned extra segment (if
+        any) is enqueued on a side stream so that it overlaps the main group."""
+        assert E.is_cuda and E.dim() == 2 and E.shape[0] == self.nmodes and E.stride(1) == 1
+        groups = plan_segments(E.shape[1], self.cfg)
+        main = torch.cuda.current_stream()
+        res = [None] * len(groups)
+        if len(groups) > 1:
+            if self.side is None:
+                self.side = torch.cuda.Stream()
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                events, self.events = self.events, None      # per-launch events only on the main stream
+                res[1] = self._run_group(E, *groups[1], wxy0, between)
+                self.events = events
+                for v in res[1].values():
+                    if torch.is_tensor(v):
+                        v.record_stream(main)
+        res[0] = self._run_group(E, *groups[0], wxy0, between)
+        if len(groups) > 1:
+            main.wait_stream(self.side)
+        return res
+
+
+def stitch(groups, key):
+    """Concatenate a per-symbol result (``eq``, ``out``, ``ph``, ``idx``) of all segments to (nmodes, N)."""
+    parts = [g[key].permute(1, 0, 2).reshape(g[key].shape[1], -1)[:, g["drop"]:] for g in groups]
+    return torch.cat(parts, dim=1)

@@ -1,0 +1,203 @@
+"""GPU parity of the batched (time-segment) device API and of every kernel variant against the CPU
+oracle on seeded synthetic inputs, plus size-independent properties at BASELINE's full C3 size."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rms(a):
+    return float(np.sqrt(np.mean(np.abs(a) ** 2))) if np.size(a) else 0.0
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import cpu_oracle as co
+    from qampy_b200 import _lib, device, pipeline, synth, theory
+    _lib.require_device()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.co, ns.device, ns.pipeline, ns.synth, ns.theory = torch, co, device, pipeline, synth, theory
+    ns.dev = torch.device("cuda", 0)
+    return ns
+
+
+@pytest.mark.parametrize("kernel", ["fast", "warp"])
+@pytest.mark.parametrize("M,ntaps,nmodes", [(64, 45, 2), (16, 21, 2), (4, 11, 1), (16, 17, 2), (64, 64, 2)])
+def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypatch):
+    """Both training kernels (8-lanes-per-stream fast path, warp-per-stream generic) on 3 segments."""
+    import qampy_b200.pythran_equalisation as pe
+    if kernel == "warp":
+        monkeypatch.setenv("QB_TRAIN_KERNEL", "warp")
+    else:
+        monkeypatch.delenv("QB_TRAIN_KERNEL", raising=False)
+    E, _ = env.synth.synth_numpy(M, 5000, nmodes=nmodes, seed=M + ntaps, snr_db=24.0)
+    t = env.torch
+    nseg, S = 3, 1500
+    Ed = t.from_numpy(E).to(env.dev)
+    Ev = env.device.segment_view(Ed, nseg, S, 2, ntaps)
+    L_seg = Ev.shape[2]
+    tr = env.theory.cal_training_symbol_len(2, ntaps, L_seg)
+    for method in ("mcma", "mrde", "cma", "rde", "sbd"):
+        sy = env.theory.reshape_symbols(None, method, M, np.complex64, nmodes)
+        w = t.from_numpy(np.tile(env.theory.init_taps(ntaps, nmodes, np.complex64), (nseg, 1, 1, 1))).to(env.dev)
+        mu = t.full((nseg, nmodes), 2e-3, dtype=t.float32, device=env.dev)
+        err = t.zeros((nseg, nmodes, tr), dtype=t.complex64, device=env.dev)
+        env.device.train_equaliser(Ev, tr, 1, 2, mu, w, None, False, t.from_numpy(sy).to(env.dev), method, err)
+        Es = np.stack([E[:, s * S * 2: s * S * 2 + L_seg] for s in range(nseg)])
+        wr = np.tile(env.theory.init_taps(ntaps, nmodes, np.complex64), (nseg, 1, 1, 1))
+        er, wr, _ = env.co.train_segments(Es, tr, 1, 2, 2e-3, wr, np.arange(nmodes), False, sy, method,
+                                          mu_shared=False)
+        assert rms(err.cpu().numpy() - er) < 1e-5 * max(1.0, rms(er)), (method, kernel)
+        assert np.max(np.abs(w.cpu().numpy() - wr)) < 2e-5, (method, kernel)
+
+
+def test_segmented_pipeline_equals_reference_per_segment(env):
+    """Every segment of the batched chain == the oracle's dual_mode_equalisation + bps on that
+    segment alone (taps, equalised symbols <= 1e-5 rms, BPS indices and phases bit exact)."""
+    t = env.torch
+    M, ntaps, S, A, N = 64, 45, 8192, 64, 45
+    E, syms = env.synth.synth_numpy(M, 30000, seed=7, snr_db=28.0)
+    cfg = env.pipeline.ReceiverConfig(M=M, ntaps=ntaps, seg_symbols=S, bps_angles=A, bps_N=N, want_err=True)
+    rx = env.pipeline.SegmentedReceiver(cfg, env.dev)
+
+    def between(eq):   # C3 recipe: phase walk inserted on the equalised 1-sps signal
+        flat = eq.reshape(-1, eq.shape[-1])
+        return env.synth.apply_phase_noise(flat, 100e3, 40e9, seed=3).reshape(eq.shape)
+
+    groups = rx.run(t.from_numpy(E).to(env.dev), between=between)
+    assert len(groups) == 2 and groups[1]["nseg"] == 1 and groups[1]["drop"] > 0
+    alphabet = env.theory.normalised_symbols(M).astype(np.complex64)
+    nout = (E.shape[1] - ntaps + 1) // 2
+    assert env.pipeline.stitch(groups, "out").shape == (2, nout)
+    worst = 0.0
+    for g in groups:
+        eq, out, ph, idx = (g[k].cpu().numpy() for k in ("eq", "out", "ph", "idx"))
+        bin_all = between(g["eq"]).cpu().numpy()
+        for s in range(g["nseg"]):
+            a = (g["first"] + s * S) * 2
+            seg = E[:, a: a + S * 2 + ntaps - 1]
+            Er, wr, (e1, e2) = env.co.dual_mode_equalisation(seg, 2, (1e-3, 1e-3), M, Ntaps=ntaps,
+                                                             methods=("mcma", "mrde"))
+            d = rms(eq[s] - Er)
+            worst = max(worst, d)
+            assert d < 1e-5
+            assert np.max(np.abs(g["taps"][s].cpu().numpy() - wr)) < 1e-5
+            assert rms(g["err"][1][s].cpu().numpy() - e2) < 1e-5
+            # BPS parity on exactly the array the GPU kernel saw
+            idr = env.co.bps_streams(bin_all[s], env.theory.bps_test_angles(A, np.float32), alphabet, N)
+            assert np.array_equal(idx[s], idr)
+            Eb, phr = env.co.bps_driver(bin_all[s], A, alphabet, N)
+            assert np.array_equal(ph[s], phr)
+            assert rms(out[s] - Eb) < 1e-6
+    # sanity: the equaliser converged and BPS fixed the phase walk (not a collapsed run)
+    assert 0.9 < rms(groups[0]["eq"].cpu().numpy()) < 1.1
+    assert env.synth.ser(groups[0]["out"][0].cpu().numpy()[:, 100:-100], syms[:, :S + 200], M) < 5e-3
+    print("worst segment rms diff", worst)
+
+
+def test_apply_batched_generic_and_fast(env):
+    t = env.torch
+    rng = np.random.default_rng(0)
+    for nmodes, ntaps, os_, modes in ((2, 45, 2, None), (2, 21, 2, [1]), (3, 7, 1, [2, 0]), (1, 11, 2, None),
+                                      (4, 9, 3, None)):
+        nseg, S = 5, 700
+        L = nseg * S * os_ + ntaps - 1
+        E = (rng.standard_normal((nmodes, L)) + 1j * rng.standard_normal((nmodes, L))).astype(np.complex64)
+        w = ((rng.standard_normal((nseg, nmodes, nmodes, ntaps)) +
+              1j * rng.standard_normal((nseg, nmodes, nmodes, ntaps))) / ntaps).astype(np.complex64)
+        Ev = env.device.segment_view(t.from_numpy(E).to(env.dev), nseg, S, os_, ntaps)
+        out = env.device.apply_filter_to_signal(Ev, os_, t.from_numpy(w).to(env.dev), modes).cpu().numpy()
+        Es = np.stack([E[:, s * S * os_: s * S * os_ + S * os_ + ntaps - 1] for s in range(nseg)])
+        ref = env.co.apply_segments(Es, os_, w, modes)
+        assert out.shape == ref.shape
+        assert rms(out - ref) < 1e-6
+    # complex128 through the generic kernel
+    E = (rng.standard_normal((2, 3000)) + 1j * rng.standard_normal((2, 3000)))
+    w = (rng.standard_normal((1, 2, 2, 45)) + 1j * rng.standard_normal((1, 2, 2, 45))) / 45
+    out = env.device.apply_filter_to_signal(t.from_numpy(E).to(env.dev)[None], 2, t.from_numpy(w).to(env.dev))
+    assert rms(out.cpu().numpy() - env.co.apply_segments(E[None], 2, w)) < 1e-13
+
+
+@pytest.mark.parametrize("M,A,N", [(32, 32, 11), (64, 64, 45), (4, 16, 5), (128, 48, 20), (256, 64, 32)])
+def test_bps_slicer_and_bruteforce_vs_oracle(env, M, A, N):
+    """Cross constellations (32/128) have no rectangular grid -> brute force; square ones use the
+    slicer, which must give the same bits as brute force and as the oracle."""
+    t = env.torch
+    rng = np.random.default_rng(M)
+    alphabet = env.theory.normalised_symbols(M).astype(np.complex64)
+    L = 3000
+    x = alphabet[rng.integers(0, M, (3, L))] + 0.05 * (rng.standard_normal((3, L)) + 1j * rng.standard_normal((3, L)))
+    x = env.synth.apply_phase_noise(t.from_numpy(x.astype(np.complex64)), 300e3, 40e9, seed=M).numpy()
+    x[2, 100] = np.nan + 0j                 # NaN and huge samples follow the reference's rules too
+    x[2, 200] = 1e20
+    tables = env.device.BpsTables(A, alphabet, np.complex64, env.dev)
+    square = int(round(np.log2(M))) % 2 == 0
+    assert (tables.n_re > 0) == square
+    xd = t.from_numpy(x).to(env.dev)
+    ref_idx = env.co.bps_streams(x, env.theory.bps_test_angles(A, np.float32), alphabet, N)
+    for use_slicer in ((True, False) if square else (False,)):
+        out, ph, idx = env.device.bps(xd, tables, N, use_slicer=use_slicer)
+        assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    for r in range(2):
+        Eb, phr = env.co.bps_driver(x[r], A, alphabet, N)
+        assert np.array_equal(ph[r].cpu().numpy(), phr)
+        assert rms(out[r].cpu().numpy() - Eb) < 1e-6
+
+
+def test_bps_edge_lengths(env):
+    """L <= 2N (no interior), L = 2N + 1, L = 1, empty."""
+    t = env.torch
+    alphabet = env.theory.normalised_symbols(16).astype(np.complex64)
+    tables = env.device.BpsTables(32, alphabet, np.complex64, env.dev)
+    rng = np.random.default_rng(1)
+    for L in (1, 7, 20, 21, 22, 64, 65):
+        x = (alphabet[rng.integers(0, 16, (1, L))] * np.exp(0.2j)).astype(np.complex64)
+        out, ph, idx = env.device.bps(t.from_numpy(x).to(env.dev), tables, 10)
+        Eb, phr = env.co.bps_driver(x[0], 32, alphabet, 10)
+        assert np.array_equal(ph[0].cpu().numpy(), phr), L
+        assert rms(out[0].cpu().numpy() - Eb) < 1e-6
+    out, ph, idx = env.device.bps(t.zeros((2, 0), dtype=t.complex64, device=env.dev), tables, 10)
+    assert out.shape == (2, 0)
+
+
+def test_full_size_c3_properties(env):
+    """BASELINE C3 size (1e7 symbols, 1220 segments): (1) segment independence -- a segment computed in
+    the big batch is bit-identical to the same segment computed alone; (2) a sampled segment matches the
+    oracle; (3) static-filter linearity; (4) BPS idempotence on already-recovered symbols' phase edges."""
+    t = env.torch
+    M, ntaps, S = 64, 45, 8192
+    E, syms = env.synth.synth_signal(M, 10 ** 7, seed=99, snr_db=28.0, device=env.dev)
+    cfg = env.pipeline.ReceiverConfig(M=M, ntaps=ntaps, seg_symbols=S)
+    rx = env.pipeline.SegmentedReceiver(cfg, env.dev)
+    groups = rx.run(E)
+    g = groups[0]
+    assert g["nseg"] == 1220
+    assert t.isfinite(t.view_as_real(g["out"])).all()
+    one = env.pipeline.SegmentedReceiver(env.pipeline.ReceiverConfig(M=M, ntaps=ntaps, seg_symbols=None), env.dev)
+    for s in (0, 517, 1219):
+        a = s * S * 2
+        seg = E[:, a: a + S * 2 + ntaps - 1].contiguous()
+        alone = one.run(seg)[0]
+        for key in ("eq", "out", "ph", "idx", "taps"):
+            assert t.equal(alone[key][0], g[key][s]), (key, s)
+    s = 901
+    seg = E[:, s * S * 2: s * S * 2 + S * 2 + ntaps - 1].cpu().numpy()
+    Er, wr, _ = env.co.dual_mode_equalisation(seg, 2, (1e-3, 1e-3), M, Ntaps=ntaps, methods=("mcma", "mrde"))
+    assert rms(g["eq"][s].cpu().numpy() - Er) < 1e-5
+    alphabet = env.theory.normalised_symbols(M).astype(np.complex64)
+    Eb, phr = env.co.bps_driver(g["eq"][s].cpu().numpy(), 64, alphabet, 45)
+    assert np.array_equal(g["ph"][s].cpu().numpy(), phr)
+    # linearity of the static filter at full size: apply(a*E1 + E2) == a*apply(E1) + apply(E2)
+    w = g["taps"][:1].contiguous()
+    E2 = t.roll(E, 12345, dims=1)
+    f = lambda x: env.device.apply_filter_to_signal(x[None], 2, w)[0]
+    lhs = f(0.5 * E + E2)
+    rhs = 0.5 * f(E) + f(E2)
+    assert float((lhs - rhs).abs().max()) < 2e-5
+    assert lhs.shape[1] == (E.shape[1] - ntaps + 1) // 2
