@@ -318,7 +318,7 @@ static int bps_check(int dtype, const void *E, int64_t nstream, int64_t L, const
                (long long)A);
     QB_REQUIRE(N >= 1, "averaging block length N must be >= 1");
     QB_REQUIRE(M >= 1 && symbols, "the symbol alphabet must not be empty");
-    QB_REQUIRE(E && comp, "E and comp must not be NULL");
+    QB_REQUIRE(comp && (E || L == 0 || nstream == 0), "E and comp must not be NULL");
     QB_REQUIRE((n_re == 0) == (n_im == 0) && n_re >= 0 && n_re <= 64 && n_im <= 64, "invalid slicer levels");
     QB_REQUIRE(n_re == 0 || n_re * n_im == M, "slicer levels do not match the alphabet size");
     QB_REQUIRE(!Eout || ph, "Eout requires ph");

@@ -316,7 +316,6 @@ int train_fast_try(TrainParams<float> p, cudaStream_t st)
 {
     if (p.os != 2) return 0;
     if (!(p.nmodes == 1 || p.nmodes == 2 || p.nmodes == 4 || p.nmodes == 8)) return 0;
-    if (p.nstreams < 8) return 0;  // too few streams to fill even one SM sub-partition: use warp-per-stream
     FastGeom g;
     g.lpp = LPS / p.nmodes;
     int nq = (p.ntaps + g.lpp - 1) / g.lpp;

@@ -100,7 +100,7 @@ class SegmentedReceiver:
         L_seg = Ev.shape[2]
         w0 = self.w0 if wxy0 is None else wxy0          # (nmodes, nmodes, ntaps): same start for all segments
         assert w0.dim() == 3, "wxy0 must be (nmodes, nmodes, ntaps)"
-        w = w0.expand(nseg, -1, -1, -1).contiguous()
+        w = w0.unsqueeze(0).repeat(nseg, 1, 1, 1)        # fresh copy per segment (trained in place)
         trsyms = theory.cal_training_symbol_len(cfg.os, cfg.ntaps, L_seg)
         errs = []
         for stage in range(len(cfg.methods)):
