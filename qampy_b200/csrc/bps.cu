@@ -39,16 +39,48 @@ struct BpsParams {
 };
 
 // Per-axis slicer.  `pairs[f] = (lev[f], lev[f+1])` are the two levels bracketing a value whose
-// (approximate) grid coordinate floors to f; the nearest level is always one of them, and because the
-// subtraction uses the STORED level values the result is bit-identical to the brute-force minimum.
+// (approximate) grid coordinate floors to f; the nearest level is always one of them (a coordinate
+// that is off by rounding near an integer still yields a bracket that contains the nearest level),
+// and because the subtraction uses the STORED level values the result is bit-identical to the
+// brute-force minimum.  The coordinate is formed with ONE FMA whose addend already carries the
+// 1.5*2^23 rounding constant, so floor() costs no conversion instruction: the integer sits in the
+// low mantissa bits.  scale = 1/step, bias = -lev0/step - 0.5 + 1.5*2^23.
 template <typename T>
-__device__ __forceinline__ T axis_min(T t, const cx<T> *pairs, int npair, T lev0, T inv_step)
+struct AxisGrid {
+    T scale, bias;
+    int npair;
+};
+__device__ __forceinline__ float axis_min(float t, const float2 *pairs, const AxisGrid<float> &g)
 {
-    T uf = floor((t - lev0) * inv_step);
-    uf = uf > (T)0 ? uf : (T)0;  // NaN -> 0
-    uf = uf < (T)(npair - 1) ? uf : (T)(npair - 1);
-    const cx<T> l = pairs[(int)uf];
-    return fmin(fabs(sub_rn(t, l.x)), fabs(sub_rn(t, l.y)));  // NaN only if t is NaN
+    const float v = fmaf(t, g.scale, g.bias);
+    int f = __float_as_int(v) - 0x4b400000;          // round-to-nearest integer of t*scale - lev0*scale - 0.5
+    f = max(0, min(f, g.npair - 1));                 // also tames huge / NaN inputs
+    const float2 l = pairs[f];
+    return fminf(fabsf(__fsub_rn(t, l.x)), fabsf(__fsub_rn(t, l.y)));  // NaN only if t is NaN
+}
+__device__ __forceinline__ double axis_min(double t, const double2 *pairs, const AxisGrid<double> &g)
+{
+    double uf = floor(fma(t, g.scale, g.bias));
+    uf = uf > 0. ? uf : 0.;
+    uf = uf < (double)(g.npair - 1) ? uf : (double)(g.npair - 1);
+    const double2 l = pairs[(int)uf];
+    return fmin(fabs(__dsub_rn(t, l.x)), fabs(__dsub_rn(t, l.y)));
+}
+__device__ __forceinline__ AxisGrid<float> make_grid(const float *lev, int n)
+{
+    AxisGrid<float> g;
+    g.npair = max(n - 1, 1);
+    g.scale = n > 1 ? (float)(n - 1) / (lev[n - 1] - lev[0]) : 0.f;
+    g.bias = -lev[0] * g.scale - 0.5f + 12582912.f;
+    return g;
+}
+__device__ __forceinline__ AxisGrid<double> make_grid(const double *lev, int n)
+{
+    AxisGrid<double> g;
+    g.npair = max(n - 1, 1);
+    g.scale = n > 1 ? (double)(n - 1) / (lev[n - 1] - lev[0]) : 0.;
+    g.bias = -lev[0] * g.scale;
+    return g;
 }
 
 template <typename T>
@@ -92,24 +124,56 @@ __device__ __forceinline__ cx<T> rotate(cx<T> e, T ph)
 }
 
 template <typename T>
+__device__ __forceinline__ T min_distance(cx<T> e, cx<T> c, bool slicer, const cx<T> *pre, const cx<T> *pim,
+                                          const AxisGrid<T> &gre, const AxisGrid<T> &gim, const cx<T> *syms,
+                                          int M)
+{
+    const T tr = sub_rn(mul_rn(e.x, c.x), mul_rn(e.y, c.y));   // E[i]*comp[a], unfused (pythran_dsp.py:79)
+    const T ti = add_rn(mul_rn(e.x, c.y), mul_rn(e.y, c.x));
+    T d;
+    if (slicer) {
+        const T da = axis_min(tr, pre, gre);
+        const T db = axis_min(ti, pim, gim);
+        d = add_rn(mul_rn(da, da), mul_rn(db, db));
+    } else {
+        d = (T)1000.;
+        for (int m = 0; m < M; m++) {
+            const cx<T> sy = syms[m];
+            const T dr = sub_rn(tr, sy.x), di = sub_rn(ti, sy.y);
+            const T dd = add_rn(mul_rn(dr, dr), mul_rn(di, di));
+            if (dd < d) d = dd;
+        }
+    }
+    return d < (T)100. ? d : (T)100.;                          // :73, :81-82
+}
+
+// One CTA walks one stream in tiles of TR = 32 rows:
+//   phase 1 (all warps)  distances of the tile -> ring[row][angle]
+//   phase 2 (A threads)  sequential running sum per angle column, window difference -> dt[angle][row]
+//   phase 3 (warp 0)     lane = row: first strict arg-min over the angles, then in the same warp the
+//                        sequential-order unwrap, the phase output and the rotation of the symbol
+// Several CTAs share an SM, so the serial phases of one stream overlap the parallel phase of another.
+constexpr int BPS_TR = 32;
+
+template <typename T>
 __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int A = p.A, W = 2 * p.N, N = p.N, TR = p.tile_rows;
-    const int RMASK = p.ring_rows - 1;  // ring_rows is a power of two >= TR + W
+    const int A = p.A, W = 2 * p.N, N = p.N;
+    constexpr int TR = BPS_TR, TRP = BPS_TR + 1;
+    const int RMASK = p.ring_rows - 1;  // ring_rows: power of two, multiple of TR, >= TR + W
     const long long L = p.L;
 
     cx<T> *comp = reinterpret_cast<cx<T> *>(smem_raw);  // [A]
-    cx<T> *syms = comp + A;                             // [M] (brute force) or level pairs (slicer)
+    cx<T> *Et = comp + A;                               // [TR] the tile's input rows
+    cx<T> *syms = Et + TR;                              // [M] (brute force) or level pairs (slicer)
     const bool slicer = p.n_re > 0;
     const int npr = slicer ? max(p.n_re - 1, 1) : 0, npi = slicer ? max(p.n_im - 1, 1) : 0;
     cx<T> *pre = syms, *pim = syms + npr;
     T *ring = reinterpret_cast<T *>(syms + (slicer ? npr + npi : p.M));  // [RR][A] running sums
-    T *dt = ring + (size_t)p.ring_rows * A;             // [TR][A] window differences
-    T *angs = dt + (size_t)TR * A;                      // [A]
-    T *p4s = angs + A;                                  // [TR] 4*angle of the tile's output rows
-    int *kidx = reinterpret_cast<int *>(p4s + TR);      // [TR]
+    T *dt = ring + (size_t)p.ring_rows * A;             // [A][TRP] window differences (transposed)
+    T *angs = dt + (size_t)A * TRP;                     // [A]
 
     const cx<T> *E = p.E + (long long)blockIdx.x * p.stream_stride;
     int32_t *idx = p.idx ? p.idx + (long long)blockIdx.x * L : nullptr;
@@ -120,16 +184,16 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
         comp[c] = p.comp[c];
         angs[c] = p.angles ? p.angles[c] : (T)0;
     }
-    T re0 = 0, rinv = 0, im0 = 0, iinv = 0;
+    AxisGrid<T> gre, gim;
+    gre.scale = gre.bias = gim.scale = gim.bias = (T)0;
+    gre.npair = gim.npair = 1;
     if (slicer) {
         for (int c = tid; c < npr; c += BPS_THREADS)
             pre[c] = make_cx<T>(p.lev_re[c], p.lev_re[min(c + 1, p.n_re - 1)]);
         for (int c = tid; c < npi; c += BPS_THREADS)
             pim[c] = make_cx<T>(p.lev_im[c], p.lev_im[min(c + 1, p.n_im - 1)]);
-        re0 = p.lev_re[0];
-        im0 = p.lev_im[0];
-        rinv = p.n_re > 1 ? (T)(p.n_re - 1) / (p.lev_re[p.n_re - 1] - re0) : (T)0;
-        iinv = p.n_im > 1 ? (T)(p.n_im - 1) / (p.lev_im[p.n_im - 1] - im0) : (T)0;
+        gre = make_grid(p.lev_re, p.n_re);
+        gim = make_grid(p.lev_im, p.n_im);
     } else {
         for (int c = tid; c < p.M; c += BPS_THREADS) syms[c] = p.symbols[c];
     }
@@ -156,113 +220,64 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
 
     T csum = 0;                 // running column sum, owned by thread a < A
     T cum = 0, p4prev = 0;      // unwrap state, replicated in warp 0
-    int slot0 = 0;              // ring slot of the tile's first row
+    int slot0 = 0;              // ring slot of the tile's first row (multiple of TR: a tile never wraps)
 
     for (long long i0 = 0; i0 < L; i0 += TR, slot0 = (slot0 + TR) & RMASK) {
         const int nrows = (int)min((long long)TR, L - i0);
+        if (tid < nrows) Et[tid] = E[i0 + tid];
+        __syncthreads();
         // ---- phase 1: distances of the tile into the ring ---------------------------------------
         if (fixed) {
-            for (int r = my_r0; r < nrows; r += rstep) {
-                const cx<T> e = E[i0 + r];
-                const T tr = sub_rn(mul_rn(e.x, my_c.x), mul_rn(e.y, my_c.y));
-                const T ti = add_rn(mul_rn(e.x, my_c.y), mul_rn(e.y, my_c.x));
-                T d;
-                if (slicer) {
-                    const T da = axis_min<T>(tr, pre, npr, re0, rinv);
-                    const T db = axis_min<T>(ti, pim, npi, im0, iinv);
-                    d = add_rn(mul_rn(da, da), mul_rn(db, db));
-                } else {
-                    d = (T)1000.;
-                    for (int m = 0; m < p.M; m++) {
-                        const cx<T> sy = syms[m];
-                        const T dr = sub_rn(tr, sy.x), di = sub_rn(ti, sy.y);
-                        const T dd = add_rn(mul_rn(dr, dr), mul_rn(di, di));
-                        if (dd < d) d = dd;
-                    }
-                }
-                ring[((slot0 + r) & RMASK) * A + my_a] = d < (T)100. ? d : (T)100.;
-            }
+            T *dst = ring + (size_t)slot0 * A + my_a;
+            for (int r = my_r0; r < nrows; r += rstep)
+                dst[r * A] = min_distance<T>(Et[r], my_c, slicer, pre, pim, gre, gim, syms, p.M);
         } else {
             for (int f = tid; f < nrows * A; f += BPS_THREADS) {
                 const int r = f / A, a = f - r * A;
-                const cx<T> e = E[i0 + r];
-                const cx<T> c = comp[a];
-                const T tr = sub_rn(mul_rn(e.x, c.x), mul_rn(e.y, c.y));
-                const T ti = add_rn(mul_rn(e.x, c.y), mul_rn(e.y, c.x));
-                T d;
-                if (slicer) {
-                    const T da = axis_min<T>(tr, pre, npr, re0, rinv);
-                    const T db = axis_min<T>(ti, pim, npi, im0, iinv);
-                    d = add_rn(mul_rn(da, da), mul_rn(db, db));
-                } else {
-                    d = (T)1000.;
-                    for (int m = 0; m < p.M; m++) {
-                        const cx<T> sy = syms[m];
-                        const T dr = sub_rn(tr, sy.x), di = sub_rn(ti, sy.y);
-                        const T dd = add_rn(mul_rn(dr, dr), mul_rn(di, di));
-                        if (dd < d) d = dd;
-                    }
-                }
-                ring[((slot0 + r) & RMASK) * A + a] = d < (T)100. ? d : (T)100.;
+                ring[(size_t)(slot0 + r) * A + a] =
+                    min_distance<T>(Et[r], comp[a], slicer, pre, pim, gre, gim, syms, p.M);
             }
         }
         __syncthreads();
         // ---- phase 2: sequential running sum per angle column + window difference ---------------
         if (tid < A) {
-            const bool full = i0 >= W && i0 > 0;   // every row of the tile has a complete window
+            T *xp = ring + (size_t)slot0 * A + tid;
+            T *dp = dt + (size_t)tid * TRP;
 #pragma unroll 4
             for (int r = 0; r < nrows; r++) {
-                T *slot = ring + ((slot0 + r) & RMASK) * A + tid;
-                const T old = ring[((slot0 + r - W) & RMASK) * A + tid];   // csum[i - W] (garbage if i < W)
-                csum = (i0 + r == 0) ? (T)0 : add_rn(csum, *slot);         // row 0 is never added (:30)
-                *slot = csum;
-                if (full || i0 + r >= W) dt[r * A + tid] = sub_rn(csum, old);
+                const T old = ring[(size_t)((slot0 + r - W) & RMASK) * A + tid];   // csum[i - W]; unused if i < W
+                csum = (i0 + r == 0) ? (T)0 : add_rn(csum, xp[r * A]);             // row 0 is never added (:30)
+                xp[r * A] = csum;
+                dp[r] = sub_rn(csum, old);
             }
         }
         __syncthreads();
-        // ---- phase 3: first strict arg-min over angles per row ----------------------------------
-        const int r_first = (int)max((long long)0, (long long)W - i0);
-        for (int r = r_first + warp; r < nrows; r += BPS_THREADS / 32) {
+        // ---- phase 3 (warp 0): arg-min, unwrap, outputs -------------------------------------------
+        // row r (lane) with i0 + r >= W produces output j = i0 + r - N; the first output overall is j = N
+        if (warp == 0) {
+            const int r = lane;
+            const long long i = i0 + r, j = i - N;
+            const bool valid = r < nrows && i >= W;
             T best = (T)1000.;
-            int bk = 0x7fffffff;
-            for (int a = lane; a < A; a += 32) {
-                const T v = dt[r * A + a];
-                if (v < best) {
+            int bk = 0;
+#pragma unroll 8
+            for (int a = 0; a < A; a++) {
+                const T v = dt[a * TRP + r];
+                if (v < best) {   // strict: first minimum, dmin0 = 1000 (:31, :39)
                     best = v;
                     bk = a;
                 }
             }
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-                const T ob = shfl_xor(best, m);
-                const int ok = shfl_xor(bk, m);
-                if (ob < best || (ob == best && ok < bk)) {
-                    best = ob;
-                    bk = ok;
-                }
-            }
-            if (lane == 0) {
-                const int k = bk == 0x7fffffff ? 0 : bk;
-                kidx[r] = k;
-                p4s[r] = mul_rn(angs[k], (T)4);
-            }
-        }
-        __syncthreads();
-        // ---- phase 4: np.unwrap(4*ph)/4 over the output rows j = i - N, sequential in fp ----------
-        // rows r >= r_first produce output j = i0 + r - N; the first output overall is j = N.
-        if (warp == 0 && ph) {
-            for (int rb = r_first; rb < nrows; rb += 32) {
-                const int r = rb + lane;
-                const bool valid = r < nrows;
-                const long long j = i0 + r - N;
-                const T p4 = valid ? p4s[r] : (T)0;
-                T pp = p4prev;                                   // lane 0: carried from the previous chunk
-                if (lane > 0 && valid) pp = p4s[r - 1];
+            if (idx && valid) idx[j] = bk;
+            if (ph) {
+                const T p4 = mul_rn(angs[bk], (T)4);
+                T pp = __shfl_up_sync(0xffffffffu, p4, 1);
+                if (lane == 0) pp = p4prev;
                 T corr = (T)0;
                 if (valid && j > N) corr = unwrap_corr<T>(p4, pp);
                 unsigned mask = __ballot_sync(0xffffffffu, corr != (T)0);
                 T mycum = cum;
-                while (mask) {
+                while (mask) {   // fold the (rare) non-zero corrections in order: exact sequential fp sum
                     const int e = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const T ce = shfl_idx(corr, e);
@@ -272,24 +287,14 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
                 const T phv = add_rn(p4, mycum) / (T)4;
                 if (valid) {
                     ph[j] = phv;
-                    p4s[r] = phv;                                // phase 5 reads the final phase from here
+                    if (Eout) Eout[j] = rotate<T>(E[j], phv);
                 }
-                const int nvalid = min(32, nrows - rb);
-                p4prev = shfl_idx(p4, nvalid - 1);
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                if (vm) p4prev = shfl_idx(p4, 31 - __clz(vm));   // last valid row of this tile
             }
         }
-        if (idx) {
-            for (int r = r_first + tid; r < nrows; r += BPS_THREADS) idx[i0 + r - N] = kidx[r];
-        }
-        // ---- phase 5: rotate the tile's output rows ----------------------------------------------
-        if (Eout) {
-            __syncthreads();
-            for (int r = r_first + tid; r < nrows; r += BPS_THREADS) {
-                const long long j = i0 + r - N;
-                Eout[j] = rotate<T>(E[j], p4s[r]);
-            }
-        }
-        __syncthreads();
+        // no barrier needed here: the next tile's first barrier orders phase 3's reads of dt against
+        // the next phase 2, and Et is only rewritten after every warp passed the phase-2 barrier
     }
 }
 
@@ -318,24 +323,13 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     p.n_im = (int)n_im;
     p.N = (int)N;
     const int W = 2 * (int)N;
-    // tile rows: fill the power-of-two ring (>= TR + 2N rows) as well as possible, keep <= ~48 KB/CTA
-    // so that several CTAs share an SM and hide each other's serial phases
-    int TR = 0, RR = 0;
-    size_t smem = 0;
-    for (int rr = 32; rr <= 65536 && !TR; rr <<= 1) {
-        if (rr <= W) continue;
-        int tr = rr - W < 64 ? rr - W : 64;
-        if (tr < 8 && rr < 65536) continue;
-        const size_t need = ((size_t)rr * A + (size_t)tr * A) * sizeof(T) +
-                            (A + (n_re ? n_re + n_im : M)) * sizeof(cx<T>) + (A + tr) * sizeof(T) +
-                            tr * sizeof(int) + 64;
-        if (need > 200 * 1024) break;
-        TR = tr;
-        RR = rr;
-        smem = need;
-    }
-    if (!TR) return set_error(QB_ERR_UNSUPPORTED, "bps: 2N*A too large for the shared-memory ring");
-    p.tile_rows = TR;
+    // ring: power of two >= TR + 2N rows (so a tile never wraps and slots are a mask away)
+    int RR = 2 * BPS_TR;
+    while (RR < BPS_TR + W) RR <<= 1;
+    const size_t smem = ((size_t)RR * A + (size_t)A * (BPS_TR + 1) + A) * sizeof(T) +
+                        (A + BPS_TR + (n_re ? n_re + n_im : M)) * sizeof(cx<T>) + 64;
+    if (smem > 200 * 1024) return set_error(QB_ERR_UNSUPPORTED, "bps: 2N*A too large for the shared-memory ring");
+    p.tile_rows = BPS_TR;
     p.ring_rows = RR;
     static bool attr_done[2] = {false, false};
     if (!attr_done[sizeof(T) == 8]) {

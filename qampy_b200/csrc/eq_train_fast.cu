@@ -74,33 +74,89 @@ __device__ __forceinline__ float walk(float signal, const float2 *parts, int np_
     return r;
 }
 
+// Per-method constants hoisted out of the symbol loop.  For rde/mrde with at most MAXC codes the
+// code/partition tables live in registers (64-QAM mrde: 4 codes + 3 boundaries per axis).
+constexpr int MAXC = 8;
+struct ErrConst {
+    float Rr, Ri;                 // cma / mcma radius constants
+    float cr[MAXC], ci[MAXC];     // codebook (real / imaginary axis tables)
+    float pr[MAXC], pi[MAXC];     // partitions; unused entries are +inf so the walk stops there
+    int in_regs;                  // tables above are valid (K small enough)
+};
+
 template <int METHOD>
-__device__ __forceinline__ float2 err_fast(int method, float2 x, const float2 *syms, int K,
+__device__ __forceinline__ ErrConst load_err_const(const float2 *syms, int K)
+{
+    ErrConst c;
+    c.Rr = K > 0 ? syms[0].x : 0.f;
+    c.Ri = K > 0 ? syms[0].y : 0.f;
+    c.in_regs = 0;
+    if (METHOD == QB_RDE || METHOD == QB_MRDE) {
+        const int nc = (K + 1) / 2, np_ = K - nc;
+        c.in_regs = nc <= MAXC;
+#pragma unroll
+        for (int j = 0; j < MAXC; j++) {
+            const bool hc = c.in_regs && j < nc, hp = c.in_regs && j < np_;
+            c.cr[j] = hc ? syms[j].x : 0.f;
+            c.ci[j] = hc ? syms[j].y : 0.f;
+            c.pr[j] = hp ? syms[nc + j].x : __int_as_float(0x7f800000);
+            c.pi[j] = hp ? syms[nc + j].y : __int_as_float(0x7f800000);
+        }
+    }
+    return c;
+}
+
+// register-table walk: `signal > +inf` is never true, so padding entries end the walk
+__device__ __forceinline__ float walk_regs(float signal, const float *parts, const float *codes)
+{
+    float r = codes[0];
+    bool alive = true;
+#pragma unroll
+    for (int j = 0; j < MAXC - 1; j++) {
+        alive = alive && (signal > parts[j]);
+        r = alive ? codes[j + 1] : r;
+    }
+    return r;
+}
+
+template <int METHOD>
+__device__ __forceinline__ float2 err_fast(int method, float2 x, const ErrConst &c, const float2 *syms, int K,
                                            const float2 *gsyms, long long i, int gl)
 {
     if (METHOD == QB_CMA) {
-        const float d = syms[0].x - (x.x * x.x + x.y * x.y);
+        const float d = c.Rr - (x.x * x.x + x.y * x.y);
         return make_float2(d * x.x, d * x.y);
     } else if (METHOD == QB_MCMA) {
-        const float dr = syms[0].x - x.x * x.x;
-        const float di = syms[0].y - x.y * x.y;
+        const float dr = c.Rr - x.x * x.x;
+        const float di = c.Ri - x.y * x.y;
         return make_float2(dr * x.x, di * x.y);
     } else if (METHOD == QB_RDE) {
-        const int nc = (K + 1) / 2;
         const float sq = x.x * x.x + x.y * x.y;
-        const float d = walk(sq, syms + nc, K - nc, syms, 0) - sq;
+        const float d = walk_regs(sq, c.pr, c.cr) - sq;
         return make_float2(x.x * d, x.y * d);
     } else if (METHOD == QB_MRDE) {
-        const int nc = (K + 1) / 2;
         const float sqr = x.x * x.x, sqi = x.y * x.y;
-        const float rr = walk(sqr, syms + nc, K - nc, syms, 0);
-        const float ri = walk(sqi, syms + nc, K - nc, syms, 1);
+        const float rr = walk_regs(sqr, c.pr, c.cr);
+        const float ri = walk_regs(sqi, c.pi, c.ci);
         return make_float2((rr - sqr) * x.x, (ri - sqi) * x.y);
     } else {
         switch (method) {
+        case QB_RDE: {  // tables too large for registers
+            const int nc = (K + 1) / 2;
+            const float sq = x.x * x.x + x.y * x.y;
+            const float d = walk(sq, syms + nc, K - nc, syms, 0) - sq;
+            return make_float2(x.x * d, x.y * d);
+        }
+        case QB_MRDE: {
+            const int nc = (K + 1) / 2;
+            const float sqr = x.x * x.x, sqi = x.y * x.y;
+            const float rr = walk(sqr, syms + nc, K - nc, syms, 0);
+            const float ri = walk(sqi, syms + nc, K - nc, syms, 1);
+            return make_float2((rr - sqr) * x.x, (ri - sqi) * x.y);
+        }
         case QB_CMA2: {
-            const float dr = syms[0].x - (x.x * x.x - x.y * x.y);
-            const float di = syms[0].y - (x.x * x.y + x.y * x.x);
+            const float dr = c.Rr - (x.x * x.x - x.y * x.y);
+            const float di = c.Ri - (x.x * x.y + x.y * x.x);
             return make_float2(dr * x.x - di * x.y, dr * x.y + di * x.x);
         }
         case QB_SBD: {
@@ -130,7 +186,9 @@ struct FastGeom {
     int nslots;     // staged segments per warp
 };
 
-template <int NQ, int METHOD>
+// NVMIN: taps q < NVMIN are valid in every lane that owns any tap (the launcher checks this), so only the
+// last NQ - NVMIN taps of a lane carry a validity predicate.
+template <int NQ, int METHOD, int NVMIN>
 __global__ void __launch_bounds__(32) train_sub8_kernel(TrainParams<float> p, FastGeom g)
 {
     static_assert(NQ % 2 == 0, "NQ must be even (os = 2 window rotation)");
@@ -172,6 +230,10 @@ __global__ void __launch_bounds__(32) train_sub8_kernel(TrainParams<float> p, Fa
     }
     float mu = p.mu[stream];
     float2 prev = make_float2(0.f, 0.f);
+    const int nvalid = min(max(p.ntaps - t0, 0), NQ);   // this lane's valid taps are q < nvalid
+    const bool adaptive = p.adaptive != 0;
+    __syncwarp();
+    const ErrConst ec = load_err_const<METHOD>(mysyms, p.K);
 
     const long long ntiles_it = (p.TrSyms + g.tile_syms - 1) / g.tile_syms;
     const long long ntiles = ntiles_it * p.Niter;
@@ -223,42 +285,48 @@ __global__ void __launch_bounds__(32) train_sub8_kernel(TrainParams<float> p, Fa
             X[q] = make_float2(v.x, v.y);
             X[q + 1] = make_float2(v.z, v.w);
         }
+        // The tile is processed in chunks of U symbols with no per-symbol branch: symbols past the end
+        // of the tile (il >= n, last chunk only) run with a zero step and are not recorded, so they
+        // change nothing.  (They read staged/zero-filled samples inside the tile buffer.)
+#pragma unroll 1
         for (int il0 = 0; il0 < n; il0 += U) {
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int il = il0 + u;
-                if (il < n) {
-                    const float4 v = *reinterpret_cast<const float4 *>(xrow + 2 * il + NQ - 2);
-                    X[(2 * u + NQ - 2) % NQ] = make_float2(v.x, v.y);
-                    X[(2 * u + NQ - 1) % NQ] = make_float2(v.z, v.w);
-                    // four independent FMA chains: re = a1 - a2, im = b1 + b2
-                    float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+                const bool live = il < n;
+                const float4 v = *reinterpret_cast<const float4 *>(xrow + 2 * il + NQ - 2);
+                X[(2 * u + NQ - 2) % NQ] = make_float2(v.x, v.y);
+                X[(2 * u + NQ - 1) % NQ] = make_float2(v.z, v.w);
+                // four independent FMA chains: re = a1 - a2, im = b1 + b2
+                float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        const float2 x = X[(2 * u + q) % NQ];
-                        a1 = fmaf(x.x, wr[q], a1);
-                        a2 = fmaf(x.y, wi[q], a2);
-                        b1 = fmaf(x.x, wi[q], b1);
-                        b2 = fmaf(x.y, wr[q], b2);
-                    }
-                    const float ar = group_sum<LPS>(a1 - a2);
-                    const float ai = group_sum<LPS>(b1 + b2);
-                    const long long i = i0 + il;
-                    const float2 e = err_fast<METHOD>(p.method, make_float2(ar, ai), mysyms, p.K, gsyms, i, gl);
-                    if (gl == 0) errs[grp * g.tile_syms + il] = e;
-                    const float cr = mu * e.x, ci = mu * e.y;
+                for (int q = 0; q < NQ; q++) {
+                    const float2 x = X[(2 * u + q) % NQ];
+                    a1 = fmaf(x.x, wr[q], a1);
+                    a2 = fmaf(x.y, wi[q], a2);
+                    b1 = fmaf(x.x, wi[q], b1);
+                    b2 = fmaf(x.y, wr[q], b2);
+                }
+                const float ar = group_sum<LPS>(a1 - a2);
+                const float ai = group_sum<LPS>(b1 + b2);
+                const long long i = i0 + il;
+                const float2 e = err_fast<METHOD>(p.method, make_float2(ar, ai), ec, mysyms, p.K, gsyms,
+                                                  live ? i : 0, gl);
+                if (gl == 0 && live) errs[grp * g.tile_syms + il] = e;
+                const float cr = live ? mu * e.x : 0.f, ci = live ? mu * e.y : 0.f;
 #pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        const float2 x = X[(2 * u + q) % NQ];
-                        if (t0 + q < p.ntaps) {  // padded taps stay exactly zero
-                            wr[q] = fmaf(cr, x.x, wr[q]);
-                            wr[q] = fmaf(ci, x.y, wr[q]);
-                            wi[q] = fmaf(ci, x.x, wi[q]);
-                            wi[q] = fmaf(-cr, x.y, wi[q]);
-                        }
+                for (int q = 0; q < NQ; q++) {
+                    const float2 x = X[(2 * u + q) % NQ];
+                    if (q < NVMIN || q < nvalid) {  // padded taps stay exactly zero
+                        wr[q] = fmaf(cr, x.x, wr[q]);
+                        wr[q] = fmaf(ci, x.y, wr[q]);
+                        wi[q] = fmaf(ci, x.x, wi[q]);
+                        wi[q] = fmaf(-cr, x.y, wi[q]);
                     }
-                    if (p.adaptive && i > 0) mu = adapt_step<float>(mu, e, prev);
-                    prev = e;
+                }
+                if (adaptive) {
+                    if (live && i > 0) mu = adapt_step<float>(mu, e, prev);
+                    if (live) prev = e;
                 }
             }
         }
@@ -277,20 +345,36 @@ __global__ void __launch_bounds__(32) train_sub8_kernel(TrainParams<float> p, Fa
     }
 }
 
-template <int NQ, int METHOD>
+template <int NQ, int METHOD, int NVMIN>
 static int launch_sub8(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
     static bool attr_done = false;
     if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(train_sub8_kernel<NQ, METHOD>,
+        QB_CUDA_CHECK(cudaFuncSetAttribute(train_sub8_kernel<NQ, METHOD, NVMIN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_done = true;
     }
     const long long nblk = (p.nstreams + GPW - 1) / GPW;
-    train_sub8_kernel<NQ, METHOD><<<(unsigned)nblk, 32, smem, st>>>(p, g);
+    train_sub8_kernel<NQ, METHOD, NVMIN><<<(unsigned)nblk, 32, smem, st>>>(p, g);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
+}
+
+template <int NQ, int METHOD>
+static int launch_sub8_pad(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
+{
+    constexpr int NVMIN = NQ > 4 ? NQ - 4 : 0;
+    // smallest number of valid taps among lanes that own at least one tap
+    int min_valid = NQ;
+    for (int j = 0; j < g.lpp; j++) {
+        const int nv = p.ntaps - j * NQ;
+        if (nv > 0 && nv < min_valid) min_valid = nv;
+    }
+    // lanes that own no tap at all have nvalid = 0 and would be (wrongly) updated for q < NVMIN
+    const bool empty_lanes = (g.lpp - 1) * NQ >= p.ntaps;
+    if (NVMIN > 0 && min_valid >= NVMIN && !empty_lanes) return launch_sub8<NQ, METHOD, NVMIN>(p, g, smem, st);
+    return launch_sub8<NQ, METHOD, 0>(p, g, smem, st);
 }
 
 template <int NQ>
@@ -299,15 +383,17 @@ static int launch_sub8_method(const TrainParams<float> &p, const FastGeom &g, si
     switch (p.method) {
     case QB_CMA:
     case QB_SGNCMA:
-        return launch_sub8<NQ, QB_CMA>(p, g, smem, st);
+        return launch_sub8_pad<NQ, QB_CMA>(p, g, smem, st);
     case QB_MCMA:
-        return launch_sub8<NQ, QB_MCMA>(p, g, smem, st);
+        return launch_sub8_pad<NQ, QB_MCMA>(p, g, smem, st);
     case QB_RDE:
-        return launch_sub8<NQ, QB_RDE>(p, g, smem, st);
+        if ((p.K + 1) / 2 > MAXC) return launch_sub8_pad<NQ, METHOD_GENERIC>(p, g, smem, st);
+        return launch_sub8_pad<NQ, QB_RDE>(p, g, smem, st);
     case QB_MRDE:
-        return launch_sub8<NQ, QB_MRDE>(p, g, smem, st);
+        if ((p.K + 1) / 2 > MAXC) return launch_sub8_pad<NQ, METHOD_GENERIC>(p, g, smem, st);
+        return launch_sub8_pad<NQ, QB_MRDE>(p, g, smem, st);
     default:
-        return launch_sub8<NQ, METHOD_GENERIC>(p, g, smem, st);
+        return launch_sub8_pad<NQ, METHOD_GENERIC>(p, g, smem, st);
     }
 }
 
