@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(32) train_sub8_kernel(TrainParams<float> p, Fa
     const int nvalid = min(max(p.ntaps - t0, 0), NQ);   // this lane's valid taps are q < nvalid
     const bool adaptive = p.adaptive != 0;
     __syncwarp();
-    const ErrConst ec = load_err_const<METHOD>(mysyms, p.K);
+    const ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);  // 0 for sbd_data: nothing staged
 
     const long long ntiles_it = (p.TrSyms + g.tile_syms - 1) / g.tile_syms;
     const long long ntiles = ntiles_it * p.Niter;
