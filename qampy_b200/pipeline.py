@@ -65,6 +65,33 @@ def shard_segments(nseg, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def max_over_ranks(value, device=None):
+    """Max of a python float over all ranks of the default process group (identity without one).
+    Used for the multi-GPU timing rule: a step takes as long as its slowest rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def rank_capture_range(nsym_total, ntaps, os, seg_symbols, rank, world):
+    """Sample range [a, b) of a long capture that ``rank`` must hold to produce ITS contiguous block of
+    segments (whole segments, ntaps-1 samples of overlap with the next rank, no exchange), plus the
+    range of output symbols it owns.  SURVEY.md section 8e."""
+    L = nsym_total * os
+    N = (L - ntaps + 1) // os
+    nseg = N // seg_symbols
+    lo, hi = shard_segments(nseg, rank, world)
+    first_sym, last_sym = lo * seg_symbols, hi * seg_symbols
+    if rank == world - 1:
+        last_sym = N                      # the last rank also takes the remainder (end-aligned extra segment)
+    a = first_sym * os
+    b = min(L, a + (last_sym - first_sym) * os + ntaps - 1) if last_sym > first_sym else a
+    return a, b, first_sym, last_sym
+
+
 class SegmentedReceiver:
     def __init__(self, cfg, dev=None, cdtype=np.complex64, nmodes=2):
         self.cfg = cfg

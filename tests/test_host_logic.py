@@ -1,0 +1,145 @@
+"""Host-side logic of the product (no GPU): constant tables, segmentation plan, argument
+validation, error mapping, patch wiring."""
+import os
+
+import numpy as np
+import pytest
+
+from qampy_b200 import _lib, pipeline, theory
+
+
+def test_theory_constants_match_reference(golden):
+    g = golden("g0_constants")
+    for M in (4, 16, 32, 64, 128, 256):
+        assert np.array_equal(theory.cal_symbols_qam(M), g["syms_%d" % M])
+        assert theory.cal_scaling_factor_qam(M) == pytest.approx(float(g["scale_%d" % M]), rel=1e-15)
+        for m in ("cma", "cma2", "sgncma", "mcma", "rde", "mrde", "sbd", "mddma", "dd"):
+            mine = theory.generate_symbols_for_eq(m, M, np.complex128)
+            ref = g["eqsyms_%s_%d" % (m, M)]
+            assert mine.shape == ref.shape
+            np.testing.assert_allclose(mine, ref, rtol=1e-14, atol=1e-15)
+            assert np.array_equal(mine.astype(np.complex64), ref.astype(np.complex64))
+    for L, nt, os_ in ((20000, 11, 2), (2000000, 21, 2), (20000000, 45, 2), (6000, 11, 2), (5000, 7, 1)):
+        assert theory.cal_training_symbol_len(os_, nt, L) == int(g["trsyms_%d_%d_%d" % (L, nt, os_)])
+
+
+def test_method_constants_survey_values():
+    # SURVEY.md section 8d "Method constants (probed, c64)"
+    assert theory.generate_symbols_for_eq("cma", 64, np.complex64)[0, 0].real == pytest.approx(1.3809524, rel=1e-6)
+    assert theory.generate_symbols_for_eq("mcma", 16, np.complex64)[0, 0] == pytest.approx(0.82 + 0.82j, rel=1e-6)
+    mr = theory.generate_symbols_for_eq("mrde", 64, np.complex64)[0]
+    np.testing.assert_allclose(mr[:4].real, [0.02380952, 0.21428572, 0.5952381, 1.1666666], rtol=1e-6)
+    np.testing.assert_allclose(mr[4:].real, [0.11904762, 0.4047619, 0.88095236], rtol=1e-6)
+    ang = theory.bps_test_angles(64, np.float32)
+    assert ang.shape == (1, 64) and ang.dtype == np.float32 and ang[0, 0] == np.float32(-np.pi / 4)
+
+
+def test_reshape_symbols_rules():
+    # qampy/core/equalisation/equalisation.py:568-594 / reference test_equalisation.py:195-291
+    s = theory.reshape_symbols(None, "mcma", 16, np.complex64, 2)
+    assert s.shape == (2, 1) and s.dtype == np.complex64
+    coded = theory.normalised_symbols(16)
+    s = theory.reshape_symbols(coded, "sbd", 16, np.complex128, 3)
+    assert s.shape == (3, 16) and np.array_equal(s[0], s[2])
+    s = theory.reshape_symbols(coded, "cma", 16, np.complex64, 2)      # non-decision: user symbols ignored
+    assert s.shape == (2, 1)
+    with pytest.raises(ValueError):
+        theory.reshape_symbols(np.zeros((3, 16), complex), "sbd", 16, np.complex64, 2)
+    with pytest.raises(ValueError):
+        theory.generate_symbols_for_eq("sbd_data", 16, np.complex64)
+    with pytest.raises(ValueError):
+        theory.generate_symbols_for_eq("nope", 16, np.complex64)
+
+
+def test_plan_segments_tiles_the_capture():
+    cfg = pipeline.ReceiverConfig(ntaps=45, os=2, seg_symbols=8192)
+    L = 2 * 10 ** 7
+    groups = pipeline.plan_segments(L, cfg)
+    N = (L - 45 + 1) // 2
+    assert groups[0] == (0, 8192, N // 8192, 0)
+    first, nsym, nseg, drop = groups[1]
+    assert nseg == 1 and nsym == 8192 and first + nsym == N and nsym - drop == N % 8192
+    # every output symbol is produced exactly once after dropping the overlap
+    assert groups[0][1] * groups[0][2] + (nsym - drop) == N
+    # last sample read stays inside the capture
+    assert (first + nsym - 1) * 2 + 45 <= L
+    assert pipeline.plan_segments(L, pipeline.ReceiverConfig(ntaps=45, seg_symbols=None)) == [(0, N, 1, 0)]
+    assert pipeline.plan_segments(2 * 8192 * 3 + 44, cfg) == [(0, 8192, 3, 0)]
+    with pytest.raises(ValueError):
+        pipeline.plan_segments(30, cfg)
+
+
+def test_shard_segments_partition():
+    for nseg in (1, 7, 1220, 1221):
+        for world in (1, 2, 4, 8):
+            spans = [pipeline.shard_segments(nseg, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == nseg
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_argument_validation_before_any_cuda_work():
+    import qampy_b200.pythran_dsp as dsp
+    import qampy_b200.pythran_equalisation as pe
+    E = np.zeros((2, 100), np.complex64)
+    w = theory.init_taps(5, 2, np.complex64)
+    sy = theory.reshape_symbols(None, "mcma", 4, np.complex64, 2)
+    with pytest.raises(ValueError, match="Unknown method"):
+        pe.train_equaliser(E, 10, 1, 2, 1e-3, w, np.arange(2), False, sy, "nope")
+    with pytest.raises(AssertionError):
+        pe.apply_filter_to_signal(E, 0, w)
+    with pytest.raises(NotImplementedError):
+        pe.apply_filter_to_signal(E.real.copy(), 2, w)
+    with pytest.raises(NotImplementedError):
+        pe.train_equaliser_realvalued()
+    with pytest.raises(NotImplementedError):
+        dsp.bps(E[0], np.zeros((100, 8), np.float32), sy[0], 4)      # per-symbol angle table
+    with pytest.raises(TypeError):
+        pe.apply_filter_to_signal(np.zeros((2, 10), np.int32), 2, w)
+
+
+def test_status_codes_map_to_reference_exceptions():
+    lib = _lib.load()
+    assert _lib.check(0) == 0 and _lib.check(3) == 3
+    assert lib.qb_method_from_name(b"mrde") == _lib.METHODS["mrde"] == 5
+    for name, code in _lib.METHODS.items():
+        assert lib.qb_method_from_name(name.encode()) == code
+    with pytest.raises(ValueError, match="Unknown method"):
+        _lib.check(lib.qb_method_from_name(b"nope"))
+    with pytest.raises(NotImplementedError):
+        _lib.check(-2)
+    with pytest.raises(MemoryError):
+        _lib.check(-4)
+    with pytest.raises(_lib.QampyB200Error):
+        _lib.check(-3)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/qampy"), reason="reference checkout not present")
+def test_patch_wires_both_seams_and_restores():
+    import sys
+    sys.path.insert(0, "/root/reference")
+    import warnings
+    warnings.filterwarnings("ignore")
+    import qampy.core.equalisation as ceq_pkg
+    import qampy.core.equalisation.equalisation as ceq
+    import qampy.core.phaserecovery as cph
+    from qampy.core.equalisation import pythran_equalisation as ref_pe
+    from qampy_b200 import patch
+    import qampy_b200.pythran_equalisation as q_pe
+    orig = (ceq.equalise_signal, ceq_pkg.dual_mode_equalisation, cph.bps, ref_pe.train_equaliser, cph._bps_idx_pyt)
+    names = patch.patch("l2")
+    assert {"equalise_signal", "dual_mode_equalisation", "apply_filter", "bps"} <= set(names)
+    assert ceq.equalise_signal is not orig[0] and ceq_pkg.dual_mode_equalisation is not orig[1]
+    assert cph.bps is not orig[2] and ref_pe.train_equaliser is orig[3]
+    patch.patch("l1")                       # re-patching first restores
+    assert ceq.equalise_signal is orig[0] and cph.bps is orig[2]
+    assert ref_pe.train_equaliser is q_pe.train_equaliser and cph._bps_idx_pyt is not orig[4]
+    patch.unpatch()
+    assert (ceq.equalise_signal, ceq_pkg.dual_mode_equalisation, cph.bps, ref_pe.train_equaliser,
+            cph._bps_idx_pyt) == orig
+    with patch.patched("l2"):
+        assert cph.bps is not orig[2]
+    assert cph.bps is orig[2]
+    with pytest.raises(ValueError):
+        patch.patch("l3")
