@@ -266,7 +266,7 @@ def run_b200(a, rank, local_rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = train_bytes / (train_ms * 1e-3) / 1e9 if train_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "train_warp_kernel<float,3> (both stages)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "train_sub_kernel (eq_train fast path, both stages)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "binding_limit": "serial recurrence latency / FP32 issue, not HBM (DESIGN.md)",

@@ -1,400 +1,29 @@
-// eq_train fast path (complex64, os = 2, nmodes in {1,2,4,8}): "8 lanes per stream".
+// Fast-path selection for eq_train (complex64, os = 2): picks how many lanes share a stream.
 //
-// Same recurrence as eq_train.cu (pythran_equalisation.py:163-172) with a layout chosen to minimise
-// instructions per trained symbol, because with thousands of independent (segment, mode) streams
-// the kernel is bound by instruction issue / FP32 FMA, not by HBM:
-//
-//   * a stream's nmodes*ntaps taps are spread over 8 lanes (4 streams per warp); lane l owns a
-//     CONTIGUOUS run of NQ taps of one input polarisation, so the samples it needs for symbol i+1 are
-//     the ones it holds for symbol i shifted by os = 2: the window lives in registers as a circular
-//     buffer and ONE 128-bit shared-memory load per symbol brings the two new samples.  The symbol
-//     loop is unrolled NQ/2 times so that the circular indexing is resolved at compile time.
-//   * the tap dot product is NQ complex MACs per lane in four independent FMA chains followed by a
-//     3-step xor-shuffle all-reduce inside the 8-lane group (instead of 5 steps over a full warp).
-//   * the error function is a template parameter for the hot methods (cma, mcma, rde, mrde): no
-//     switch in the loop; the partition walk of rde/mrde (pythran_equalisation.py:4-9) is evaluated
-//     branch-free with loads that do not depend on the equaliser output.
-//   * the two modes of a segment sit in adjacent groups of the same warp and share one staged copy of
-//     the segment's samples; tiles are double buffered with 128-bit cp.async issued by all 32 lanes.
+// With few streams the kernel is latency bound (one warp per SM sub-partition cannot hide its own
+// dependent chain), with thousands it is bound by instruction issue.  Fewer lanes per stream means
+// fewer instructions per trained symbol (shorter shuffle reduction, more register-window reuse) but
+// also fewer warps; so the widest layout that still leaves about two warps per sub-partition wins.
+#include <stdlib.h>
+
 #include "eq_train_common.cuh"
 
 namespace qb {
 
-constexpr int LPS = 8;         // lanes per stream
-constexpr int GPW = 32 / LPS;  // streams (groups) per warp
-constexpr int METHOD_GENERIC = -1;
+int train_fast_l8(TrainParams<float> p, cudaStream_t st);
+int train_fast_l16(TrainParams<float> p, cudaStream_t st);
+int train_fast_l32(TrainParams<float> p, cudaStream_t st);
 
-template <int W>
-__device__ __forceinline__ float group_sum(float v)
+static int sm_count()
 {
-#pragma unroll
-    for (int m = W / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    return v;
-}
-
-// first strict minimum over the alphabet inside an 8-lane group (pythran_equalisation.py:240-265)
-__device__ __forceinline__ float2 det_symbol_group(float2 x, const float2 *syms, int K, int gl)
-{
-    float best = 1000.f;
-    int bj = 0x7fffffff;
-    for (int j = gl; j < K; j += LPS) {
-        const float2 s = syms[j];
-        const float dr = x.x - s.x, di = x.y - s.y;
-        const float d = dr * dr + di * di;
-        if (d < best) {
-            best = d;
-            bj = j;
-        }
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
     }
-#pragma unroll
-    for (int m = LPS / 2; m >= 1; m >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, m);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, m);
-        if (ob < best || (ob == best && oj < bj)) {
-            best = ob;
-            bj = oj;
-        }
-    }
-    if (bj == 0x7fffffff) return make_float2(1.f, 0.f);
-    return syms[bj];
-}
-
-// branch-free partition walk: index = number of leading partitions the signal exceeds
-__device__ __forceinline__ float walk(float signal, const float2 *parts, int np_, const float2 *codes,
-                                      int part)
-{
-    float r = part ? codes[0].y : codes[0].x;
-    bool alive = true;
-    for (int j = 0; j < np_; j++) {
-        const float pj = part ? parts[j].y : parts[j].x;
-        const float cj = part ? codes[j + 1].y : codes[j + 1].x;
-        alive = alive && (signal > pj);
-        r = alive ? cj : r;
-    }
-    return r;
-}
-
-// Per-method constants hoisted out of the symbol loop.  For rde/mrde with at most MAXC codes the
-// code/partition tables live in registers (64-QAM mrde: 4 codes + 3 boundaries per axis).
-constexpr int MAXC = 8;
-struct ErrConst {
-    float Rr, Ri;                 // cma / mcma radius constants
-    float cr[MAXC], ci[MAXC];     // codebook (real / imaginary axis tables)
-    float pr[MAXC], pi[MAXC];     // partitions; unused entries are +inf so the walk stops there
-    int in_regs;                  // tables above are valid (K small enough)
-};
-
-template <int METHOD>
-__device__ __forceinline__ ErrConst load_err_const(const float2 *syms, int K)
-{
-    ErrConst c;
-    c.Rr = K > 0 ? syms[0].x : 0.f;
-    c.Ri = K > 0 ? syms[0].y : 0.f;
-    c.in_regs = 0;
-    if (METHOD == QB_RDE || METHOD == QB_MRDE) {
-        const int nc = (K + 1) / 2, np_ = K - nc;
-        c.in_regs = nc <= MAXC;
-#pragma unroll
-        for (int j = 0; j < MAXC; j++) {
-            const bool hc = c.in_regs && j < nc, hp = c.in_regs && j < np_;
-            c.cr[j] = hc ? syms[j].x : 0.f;
-            c.ci[j] = hc ? syms[j].y : 0.f;
-            c.pr[j] = hp ? syms[nc + j].x : __int_as_float(0x7f800000);
-            c.pi[j] = hp ? syms[nc + j].y : __int_as_float(0x7f800000);
-        }
-    }
-    return c;
-}
-
-// register-table walk: `signal > +inf` is never true, so padding entries end the walk
-__device__ __forceinline__ float walk_regs(float signal, const float *parts, const float *codes)
-{
-    float r = codes[0];
-    bool alive = true;
-#pragma unroll
-    for (int j = 0; j < MAXC - 1; j++) {
-        alive = alive && (signal > parts[j]);
-        r = alive ? codes[j + 1] : r;
-    }
-    return r;
-}
-
-template <int METHOD>
-__device__ __forceinline__ float2 err_fast(int method, float2 x, const ErrConst &c, const float2 *syms, int K,
-                                           const float2 *gsyms, long long i, int gl)
-{
-    if (METHOD == QB_CMA) {
-        const float d = c.Rr - (x.x * x.x + x.y * x.y);
-        return make_float2(d * x.x, d * x.y);
-    } else if (METHOD == QB_MCMA) {
-        const float dr = c.Rr - x.x * x.x;
-        const float di = c.Ri - x.y * x.y;
-        return make_float2(dr * x.x, di * x.y);
-    } else if (METHOD == QB_RDE) {
-        const float sq = x.x * x.x + x.y * x.y;
-        const float d = walk_regs(sq, c.pr, c.cr) - sq;
-        return make_float2(x.x * d, x.y * d);
-    } else if (METHOD == QB_MRDE) {
-        const float sqr = x.x * x.x, sqi = x.y * x.y;
-        const float rr = walk_regs(sqr, c.pr, c.cr);
-        const float ri = walk_regs(sqi, c.pi, c.ci);
-        return make_float2((rr - sqr) * x.x, (ri - sqi) * x.y);
-    } else {
-        switch (method) {
-        case QB_RDE: {  // tables too large for registers
-            const int nc = (K + 1) / 2;
-            const float sq = x.x * x.x + x.y * x.y;
-            const float d = walk(sq, syms + nc, K - nc, syms, 0) - sq;
-            return make_float2(x.x * d, x.y * d);
-        }
-        case QB_MRDE: {
-            const int nc = (K + 1) / 2;
-            const float sqr = x.x * x.x, sqi = x.y * x.y;
-            const float rr = walk(sqr, syms + nc, K - nc, syms, 0);
-            const float ri = walk(sqi, syms + nc, K - nc, syms, 1);
-            return make_float2((rr - sqr) * x.x, (ri - sqi) * x.y);
-        }
-        case QB_CMA2: {
-            const float dr = c.Rr - (x.x * x.x - x.y * x.y);
-            const float di = c.Ri - (x.x * x.y + x.y * x.x);
-            return make_float2(dr * x.x - di * x.y, dr * x.y + di * x.x);
-        }
-        case QB_SBD: {
-            const float2 s = det_symbol_group(x, syms, K, gl);
-            return make_float2((s.x - x.x) * fabsf(s.x), (s.y - x.y) * fabsf(s.y));
-        }
-        case QB_SBD_DATA: {
-            const float2 s = gsyms[i];
-            return make_float2((s.x - x.x) * fabsf(s.x), (s.y - x.y) * fabsf(s.y));
-        }
-        case QB_MDDMA: {
-            const float2 s = det_symbol_group(x, syms, K, gl);
-            return make_float2((s.x * s.x - x.x * x.x) * x.x, (s.y * s.y - x.y * x.y) * x.y);
-        }
-        default: {  // QB_DD
-            const float2 s = det_symbol_group(x, syms, K, gl);
-            return make_float2(s.x - x.x, s.y - x.y);
-        }
-        }
-    }
-}
-
-struct FastGeom {
-    int lpp;        // lanes per input polarisation = LPS / nmodes
-    int tile_syms;  // multiple of NQ/2
-    int pitch;      // samples per staged row (even)
-    int nslots;     // staged segments per warp
-};
-
-// NVMIN: taps q < NVMIN are valid in every lane that owns any tap (the launcher checks this), so only the
-// last NQ - NVMIN taps of a lane carry a validity predicate.
-template <int NQ, int METHOD, int NVMIN>
-__global__ void __launch_bounds__(32) train_sub8_kernel(TrainParams<float> p, FastGeom g)
-{
-    static_assert(NQ % 2 == 0, "NQ must be even (os = 2 window rotation)");
-    constexpr int U = NQ / 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x, grp = lane / LPS, gl = lane % LPS;
-    const long long stream0 = (long long)blockIdx.x * GPW;
-    const bool active = stream0 + grp < p.nstreams;
-    const long long stream = active ? stream0 + grp : p.nstreams - 1;
-    const long long seg = stream / p.nsel;
-    const int jsel = (int)(stream % p.nsel);
-    const int mode = p.modes.m[jsel];
-    const long long seg_first = stream0 / p.nsel;
-    const long long seg_last = min(stream0 + GPW - 1, p.nstreams - 1) / p.nsel;
-    const int nslots = (int)(seg_last - seg_first) + 1;
-    const int slot = (int)(seg - seg_first);
-
-    const int slot_samples = p.nmodes * g.pitch;
-    float2 *tile0 = reinterpret_cast<float2 *>(smem_raw);
-    float2 *tile1 = tile0 + g.nslots * slot_samples;
-    float2 *errs = tile1 + g.nslots * slot_samples;  // [GPW][tile_syms]
-    float2 *syms = errs + GPW * g.tile_syms;         // [nsym_smem]
-
-    const float2 *gsyms = p.symbols + (long long)mode * p.K;
-    // every group may train a different mode -> per-group copy of the (small) constant table
-    float2 *mysyms = syms + grp * p.nsym_smem;
-    for (int c = gl; c < p.nsym_smem; c += LPS) mysyms[c] = gsyms[c];
-
-    // lane -> (input polarisation k, first tap t0); taps t0 .. t0+NQ-1, valid while < ntaps
-    const int k = gl / g.lpp, t0 = (gl % g.lpp) * NQ;
-    float wr[NQ], wi[NQ];
-    float2 *wg = p.wx + ((long long)seg * p.nmodes + mode) * (long long)(p.nmodes * p.ntaps) + k * p.ntaps;
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        const bool valid = t0 + q < p.ntaps;
-        const float2 w = valid ? wg[t0 + q] : make_float2(0.f, 0.f);
-        wr[q] = w.x;
-        wi[q] = w.y;
-    }
-    float mu = p.mu[stream];
-    float2 prev = make_float2(0.f, 0.f);
-    const int nvalid = min(max(p.ntaps - t0, 0), NQ);   // this lane's valid taps are q < nvalid
-    const bool adaptive = p.adaptive != 0;
-    __syncwarp();
-    const ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);  // 0 for sbd_data: nothing staged
-
-    const long long ntiles_it = (p.TrSyms + g.tile_syms - 1) / g.tile_syms;
-    const long long ntiles = ntiles_it * p.Niter;
-    const long long Lread = (p.TrSyms - 1) * 2 + p.ntaps;  // samples of a row the caller guarantees
-    const bool al16 = ((reinterpret_cast<uintptr_t>(p.E) & 15) == 0) && (p.seg_stride % 2 == 0) &&
-                      (p.row_stride % 2 == 0);
-
-    auto load_tile = [&](long long gt, float2 *buf) {
-        const long long i0 = (gt % ntiles_it) * g.tile_syms;
-        const long long s0 = i0 * 2;                                   // first sample of the tile (even)
-        const int have = (int)max(0LL, min((long long)g.pitch, Lread - s0));  // samples that exist
-        for (int sl = 0; sl < nslots; sl++) {
-            for (int kk = 0; kk < p.nmodes; kk++) {
-                const float2 *src = p.E + (seg_first + sl) * p.seg_stride + (long long)kk * p.row_stride + s0;
-                float2 *dst = buf + sl * slot_samples + kk * g.pitch;
-                if (al16) {
-                    const int npair = have >> 1;
-                    for (int c = lane; c < npair; c += 32) cp_async<16>(dst + 2 * c, src + 2 * c);
-                    if ((have & 1) && lane == 0) cp_async<8>(dst + have - 1, src + have - 1);
-                } else {
-                    for (int c = lane; c < have; c += 32) cp_async<8>(dst + c, src + c);
-                }
-                for (int c = have + lane; c < g.pitch; c += 32) dst[c] = make_float2(0.f, 0.f);
-            }
-        }
-        cp_async_commit();
-    };
-
-    if (ntiles > 0) load_tile(0, tile0);
-    for (long long gt = 0; gt < ntiles; gt++) {
-        float2 *cur = (gt & 1) ? tile1 : tile0;
-        if (gt + 1 < ntiles) {
-            load_tile(gt + 1, (gt & 1) ? tile0 : tile1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncwarp();
-        const long long it = gt / ntiles_it;
-        const long long i0 = (gt % ntiles_it) * g.tile_syms;
-        const int n = (int)min((long long)g.tile_syms, p.TrSyms - i0);
-        const float2 *xrow = cur + slot * slot_samples + k * g.pitch + t0;  // 16B aligned (t0, pitch even)
-
-        // circular register window: sample at tile-local position (2*il + q) sits in X[(2u+q) % NQ]
-        float2 X[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ - 2; q += 2) {
-            const float4 v = *reinterpret_cast<const float4 *>(xrow + q);
-            X[q] = make_float2(v.x, v.y);
-            X[q + 1] = make_float2(v.z, v.w);
-        }
-        // The tile is processed in chunks of U symbols with no per-symbol branch: symbols past the end
-        // of the tile (il >= n, last chunk only) run with a zero step and are not recorded, so they
-        // change nothing.  (They read staged/zero-filled samples inside the tile buffer.)
-#pragma unroll 1
-        for (int il0 = 0; il0 < n; il0 += U) {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int il = il0 + u;
-                const bool live = il < n;
-                const float4 v = *reinterpret_cast<const float4 *>(xrow + 2 * il + NQ - 2);
-                X[(2 * u + NQ - 2) % NQ] = make_float2(v.x, v.y);
-                X[(2 * u + NQ - 1) % NQ] = make_float2(v.z, v.w);
-                // four independent FMA chains: re = a1 - a2, im = b1 + b2
-                float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    const float2 x = X[(2 * u + q) % NQ];
-                    a1 = fmaf(x.x, wr[q], a1);
-                    a2 = fmaf(x.y, wi[q], a2);
-                    b1 = fmaf(x.x, wi[q], b1);
-                    b2 = fmaf(x.y, wr[q], b2);
-                }
-                const float ar = group_sum<LPS>(a1 - a2);
-                const float ai = group_sum<LPS>(b1 + b2);
-                const long long i = i0 + il;
-                const float2 e = err_fast<METHOD>(p.method, make_float2(ar, ai), ec, mysyms, p.K, gsyms,
-                                                  live ? i : 0, gl);
-                if (gl == 0 && live) errs[grp * g.tile_syms + il] = e;
-                const float cr = live ? mu * e.x : 0.f, ci = live ? mu * e.y : 0.f;
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    const float2 x = X[(2 * u + q) % NQ];
-                    if (q < NVMIN || q < nvalid) {  // padded taps stay exactly zero
-                        wr[q] = fmaf(cr, x.x, wr[q]);
-                        wr[q] = fmaf(ci, x.y, wr[q]);
-                        wi[q] = fmaf(ci, x.x, wi[q]);
-                        wi[q] = fmaf(-cr, x.y, wi[q]);
-                    }
-                }
-                if (adaptive) {
-                    if (live && i > 0) mu = adapt_step<float>(mu, e, prev);
-                    if (live) prev = e;
-                }
-            }
-        }
-        __syncwarp();
-        if (p.err && active) {
-            float2 *eg = p.err + ((long long)seg * p.nmodes + mode) * (p.TrSyms * p.Niter) + it * p.TrSyms + i0;
-            for (int c = gl; c < n; c += LPS) eg[c] = errs[grp * g.tile_syms + c];
-        }
-        __syncwarp();
-    }
-    if (active) {
-#pragma unroll
-        for (int q = 0; q < NQ; q++)
-            if (t0 + q < p.ntaps) wg[t0 + q] = make_float2(wr[q], wi[q]);
-        if (gl == 0) p.mu[stream] = mu;
-    }
-}
-
-template <int NQ, int METHOD, int NVMIN>
-static int launch_sub8(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
-{
-    static bool attr_done = false;
-    if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(train_sub8_kernel<NQ, METHOD, NVMIN>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_done = true;
-    }
-    const long long nblk = (p.nstreams + GPW - 1) / GPW;
-    train_sub8_kernel<NQ, METHOD, NVMIN><<<(unsigned)nblk, 32, smem, st>>>(p, g);
-    count_launch();
-    QB_CUDA_CHECK(cudaGetLastError());
-    return QB_OK;
-}
-
-template <int NQ, int METHOD>
-static int launch_sub8_pad(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
-{
-    constexpr int NVMIN = NQ > 4 ? NQ - 4 : 0;
-    // smallest number of valid taps among lanes that own at least one tap
-    int min_valid = NQ;
-    for (int j = 0; j < g.lpp; j++) {
-        const int nv = p.ntaps - j * NQ;
-        if (nv > 0 && nv < min_valid) min_valid = nv;
-    }
-    // lanes that own no tap at all have nvalid = 0 and would be (wrongly) updated for q < NVMIN
-    const bool empty_lanes = (g.lpp - 1) * NQ >= p.ntaps;
-    if (NVMIN > 0 && min_valid >= NVMIN && !empty_lanes) return launch_sub8<NQ, METHOD, NVMIN>(p, g, smem, st);
-    return launch_sub8<NQ, METHOD, 0>(p, g, smem, st);
-}
-
-template <int NQ>
-static int launch_sub8_method(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
-{
-    switch (p.method) {
-    case QB_CMA:
-    case QB_SGNCMA:
-        return launch_sub8_pad<NQ, QB_CMA>(p, g, smem, st);
-    case QB_MCMA:
-        return launch_sub8_pad<NQ, QB_MCMA>(p, g, smem, st);
-    case QB_RDE:
-        if ((p.K + 1) / 2 > MAXC) return launch_sub8_pad<NQ, METHOD_GENERIC>(p, g, smem, st);
-        return launch_sub8_pad<NQ, QB_RDE>(p, g, smem, st);
-    case QB_MRDE:
-        if ((p.K + 1) / 2 > MAXC) return launch_sub8_pad<NQ, METHOD_GENERIC>(p, g, smem, st);
-        return launch_sub8_pad<NQ, QB_MRDE>(p, g, smem, st);
-    default:
-        return launch_sub8_pad<NQ, METHOD_GENERIC>(p, g, smem, st);
-    }
+    return n;
 }
 
 // Returns 1 if the fast path took the job, 0 if the shape is outside it (caller falls back), <0 on error.
@@ -402,31 +31,29 @@ int train_fast_try(TrainParams<float> p, cudaStream_t st)
 {
     if (p.os != 2) return 0;
     if (!(p.nmodes == 1 || p.nmodes == 2 || p.nmodes == 4 || p.nmodes == 8)) return 0;
-    FastGeom g;
-    g.lpp = LPS / p.nmodes;
-    int nq = (p.ntaps + g.lpp - 1) / g.lpp;
-    nq += nq & 1;
-    if (nq > 16) return 0;
-    if (nq == 10) nq = 12;
-    if (nq == 14) nq = 16;
-    const int U = nq / 2;
-    g.tile_syms = (64 / U) * U;
-    g.pitch = ((g.tile_syms - 1) * 2 + g.lpp * nq + 1) & ~1;
-    g.nslots = (GPW % p.nsel == 0) ? GPW / p.nsel : min(GPW, GPW / p.nsel + 2);
     p.nsym_smem = (p.method == QB_SBD_DATA) ? 0 : p.K;
-    const size_t smem = ((size_t)2 * g.nslots * p.nmodes * g.pitch + (size_t)GPW * g.tile_syms +
-                         (size_t)GPW * p.nsym_smem) * sizeof(float2);
-    if (smem > 64 * 1024) return 0;
-    int rc;
-    switch (nq) {
-    case 2: rc = launch_sub8_method<2>(p, g, smem, st); break;
-    case 4: rc = launch_sub8_method<4>(p, g, smem, st); break;
-    case 6: rc = launch_sub8_method<6>(p, g, smem, st); break;
-    case 8: rc = launch_sub8_method<8>(p, g, smem, st); break;
-    case 12: rc = launch_sub8_method<12>(p, g, smem, st); break;
-    default: rc = launch_sub8_method<16>(p, g, smem, st); break;
+    // QB_TRAIN_LPS = 8 | 16 | 32 forces a layout (tests, tuning)
+    int forced = 0;
+    if (const char *e = getenv("QB_TRAIN_LPS")) forced = atoi(e);
+    const long long target_warps = 2LL * 4 * sm_count();   // ~2 warps per SM sub-partition
+    int order[3];
+    if (forced == 8 || forced == 16 || forced == 32) {
+        order[0] = forced; order[1] = forced == 8 ? 16 : 8; order[2] = forced == 32 ? 16 : 32;
+    } else if (p.nstreams * 8 / 32 >= target_warps) {
+        order[0] = 8; order[1] = 16; order[2] = 32;
+    } else if (p.nstreams * 16 / 32 >= target_warps / 2) {
+        order[0] = 16; order[1] = 8; order[2] = 32;
+    } else {
+        order[0] = 8; order[1] = 16; order[2] = 32;    // few streams: fewest instructions per symbol
     }
-    return rc == QB_OK ? 1 : rc;
+    for (int k = 0; k < 3; k++) {
+        int rc = 0;
+        if (order[k] == 8) rc = train_fast_l8(p, st);
+        if (order[k] == 16) rc = train_fast_l16(p, st);
+        if (order[k] == 32) rc = train_fast_l32(p, st);
+        if (rc != 0) return rc;
+    }
+    return 0;
 }
 
 }  // namespace qb

@@ -27,15 +27,17 @@ def env():
     return ns
 
 
-@pytest.mark.parametrize("kernel", ["fast", "warp"])
+@pytest.mark.parametrize("kernel", ["lps8", "lps16", "lps32", "warp"])
 @pytest.mark.parametrize("M,ntaps,nmodes", [(64, 45, 2), (16, 21, 2), (4, 11, 1), (16, 17, 2), (64, 64, 2)])
 def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypatch):
-    """Both training kernels (8-lanes-per-stream fast path, warp-per-stream generic) on 3 segments."""
+    """Every training kernel layout (8/16/32 lanes per stream fast path, warp-per-stream generic), 3 segments."""
     import qampy_b200.pythran_equalisation as pe
+    monkeypatch.delenv("QB_TRAIN_KERNEL", raising=False)
+    monkeypatch.delenv("QB_TRAIN_LPS", raising=False)
     if kernel == "warp":
         monkeypatch.setenv("QB_TRAIN_KERNEL", "warp")
     else:
-        monkeypatch.delenv("QB_TRAIN_KERNEL", raising=False)
+        monkeypatch.setenv("QB_TRAIN_LPS", kernel[3:])
     E, _ = env.synth.synth_numpy(M, 5000, nmodes=nmodes, seed=M + ntaps, snr_db=24.0)
     t = env.torch
     nseg, S = 3, 1500
