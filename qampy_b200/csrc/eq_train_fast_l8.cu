@@ -1,5 +1,7 @@
-// Instantiations of the LPS = 8 lanes-per-stream training kernel (see eq_train_fast.cuh).
-#include "eq_train_fast.cuh"
+// Instantiations of the LPS = 8 lanes-per-stream training kernels (eq_train_fast.cuh, eq_train_la.cuh).
+#include <stdlib.h>
+
+#include "eq_train_la.cuh"
 
 namespace qb {
 
@@ -10,6 +12,21 @@ int train_fast_l8(TrainParams<float> p, cudaStream_t st)
     size_t smem = 0;
     const int nq = fast_geometry<8>(p, g, smem, 16);
     if (!nq) return 0;
+    // QB_TRAIN_LA=0 disables the look-ahead kernel (parity tests run both forms)
+    const char *la = getenv("QB_TRAIN_LA");
+    if (!(la && la[0] == '0')) {
+        int r = 0;
+        switch (nq) {
+        case 2: r = try_la<8, 2>(p, g, st); break;
+        case 4: r = try_la<8, 4>(p, g, st); break;
+        case 6: r = try_la<8, 6>(p, g, st); break;
+        case 8: r = try_la<8, 8>(p, g, st); break;
+        case 12: r = try_la<8, 12>(p, g, st); break;
+        case 16: r = try_la<8, 16>(p, g, st); break;
+        default: break;
+        }
+        if (r != 0) return r;
+    }
     int rc;
     switch (nq) {
     case 2: rc = launch_sub_method<8, 2>(p, g, smem, st); break;

@@ -27,16 +27,20 @@ def env():
     return ns
 
 
-@pytest.mark.parametrize("kernel", ["lps8", "lps16", "lps32", "warp"])
+@pytest.mark.parametrize("kernel", ["la8", "lps8", "lps16", "warp"])
 @pytest.mark.parametrize("M,ntaps,nmodes", [(64, 45, 2), (16, 21, 2), (4, 11, 1), (16, 17, 2), (64, 64, 2)])
 def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypatch):
-    """Every training kernel layout (8/16/32 lanes per stream fast path, warp-per-stream generic), 3 segments."""
+    """Every training kernel (look-ahead and direct form with 8 lanes per stream, 16 lanes per stream,
+    generic warp per stream) on 3 segments, all error functions with a dedicated code path."""
     import qampy_b200.pythran_equalisation as pe
-    monkeypatch.delenv("QB_TRAIN_KERNEL", raising=False)
-    monkeypatch.delenv("QB_TRAIN_LPS", raising=False)
+    for var in ("QB_TRAIN_KERNEL", "QB_TRAIN_LPS", "QB_TRAIN_LA"):
+        monkeypatch.delenv(var, raising=False)
     if kernel == "warp":
         monkeypatch.setenv("QB_TRAIN_KERNEL", "warp")
+    elif kernel == "la8":
+        pass                                          # default: 8 lanes per stream, look-ahead form
     else:
+        monkeypatch.setenv("QB_TRAIN_LA", "0")        # direct form of the recurrence
         monkeypatch.setenv("QB_TRAIN_LPS", kernel[3:])
     E, _ = env.synth.synth_numpy(M, 5000, nmodes=nmodes, seed=M + ntaps, snr_db=24.0)
     t = env.torch
