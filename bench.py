@@ -39,7 +39,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nsym", type=int, default=10 ** 7, help="symbols per polarisation per GPU")
-    ap.add_argument("--seg", type=int, default=8192, help="output symbols per segment (0 = one segment)")
+    ap.add_argument("--seg", type=int, default=-1,
+                    help="output symbols per segment; -1 = smallest length >= 8192 that fills whole GPU waves "
+                         "(pipeline.balanced_segment_symbols), 0 = one segment")
+    ap.add_argument("--chunks", type=int, default=8, help="host<->device overlap chunks of the e2e path")
     ap.add_argument("--ntaps", type=int, default=45)
     ap.add_argument("--M", type=int, default=64)
     ap.add_argument("--angles", type=int, default=64)
@@ -277,25 +280,19 @@ def run_b200(a, rank, local_rank, world):
                               "bps": BYTES_BPS * nsym_out / (sum(per.get("bps", [0])) / a.steps * 1e-3) / 1e9
                               if per.get("bps") else None}}
 
-    # end to end: pinned host input -> H2D -> chain -> D2H of the recovered symbols + phase
+    # end to end: pinned host capture -> H2D -> chain -> D2H of the recovered symbols + phase, with
+    # the copies of neighbouring chunks overlapping the compute (pipeline.run_host)
     e2e = None
     if not a.no_e2e:
         Eh = torch.empty(E.shape, dtype=E.dtype, pin_memory=True)
         Eh.copy_(E)
         Ed = torch.empty_like(E)
-        outs_h = None
+        outs = (None, None)
         times = []
         for it in range(2 + a.steps):
             barrier()
             t0 = time.perf_counter()
-            Ed.copy_(Eh, non_blocking=True)
-            res = rx.run(Ed)
-            if outs_h is None:
-                outs_h = [(torch.empty(g["out"].shape, dtype=g["out"].dtype, pin_memory=True),
-                           torch.empty(g["ph"].shape, dtype=g["ph"].dtype, pin_memory=True)) for g in res]
-            for g, (oh, ph) in zip(res, outs_h):
-                oh.copy_(g["out"], non_blocking=True)
-                ph.copy_(g["ph"], non_blocking=True)
+            outs = pipeline.run_host(rx, Eh, outs[0], outs[1], nchunks=a.chunks, E_dev=Ed)[:2]
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if it >= 2:
@@ -306,10 +303,15 @@ def run_b200(a, rank, local_rank, world):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t = float(tt.item())
         h2d = E.numel() * E.element_size()
-        d2h = sum(o.numel() * o.element_size() + p.numel() * p.element_size() for o, p in outs_h)
+        d2h = sum(o.numel() * o.element_size() for o in outs)
+        # the overlapped path must give the same symbols as the device-resident one
+        chk = rx.run(E)
+        same = bool(torch.equal(outs[0][:chk[0]["nseg"]].to(dev), chk[0]["out"]))
         e2e = {"value": world * L / t / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": t * 1e3,
-               "api": "pinned host capture -> qampy_b200.pipeline.SegmentedReceiver.run -> pinned host symbols+phase"}
+               "d2h_bytes_per_step": d2h, "ms_per_step": t * 1e3, "chunks": a.chunks,
+               "matches_device_path": same,
+               "api": "pinned host capture -> qampy_b200.pipeline.run_host (H2D / chain / D2H overlapped per "
+                      "chunk of segments) -> pinned host symbols + phase"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps,
@@ -327,8 +329,17 @@ def run_b200(a, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def resolve_segments(a):
+    """--seg -1: balanced segment length for this capture (same value for the GPU and the CPU arm)."""
+    if a.seg < 0:
+        from qampy_b200 import pipeline
+        cfg = pipeline.ReceiverConfig(M=a.M, ntaps=a.ntaps, os=2)
+        a.seg = pipeline.balanced_segment_symbols(2 * a.nsym, cfg, target=8192)
+    return a
+
+
 def main():
-    a = parse()
+    a = resolve_segments(parse())
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -12,17 +12,15 @@ int train_fast_l8(TrainParams<float> p, cudaStream_t st)
     size_t smem = 0;
     const int nq = fast_geometry<8>(p, g, smem, 16);
     if (!nq) return 0;
-    // QB_TRAIN_LA=0 disables the look-ahead kernel (parity tests run both forms)
+    // QB_TRAIN_LA=1 selects the look-ahead form of the recurrence (eq_train_la.cuh).  It is exact algebra
+    // and parity-tested, but measured SLOWER than the direct form on B200 (394 vs 310 cycles per symbol,
+    // profiles/README.md): ptxas does not overlap the extra work with the shuffle latency.  Kept opt-in.
     const char *la = getenv("QB_TRAIN_LA");
-    if (!(la && la[0] == '0')) {
+    if (la && la[0] == '1') {
         int r = 0;
         switch (nq) {
-        case 2: r = try_la<8, 2>(p, g, st); break;
-        case 4: r = try_la<8, 4>(p, g, st); break;
         case 6: r = try_la<8, 6>(p, g, st); break;
-        case 8: r = try_la<8, 8>(p, g, st); break;
         case 12: r = try_la<8, 12>(p, g, st); break;
-        case 16: r = try_la<8, 16>(p, g, st); break;
         default: break;
         }
         if (r != 0) return r;

@@ -58,6 +58,30 @@ def plan_segments(L, cfg):
     return groups
 
 
+def balanced_segment_symbols(L, cfg, target=8192, nmodes=2, n_sm=148, streams_per_warp=4, warps_per_sm=4):
+    """Segment length >= ``target`` for which the trained streams fill whole waves of the GPU.
+
+    The training kernel runs ``streams_per_warp`` (segment, mode) streams per warp and is latency bound:
+    a launch takes as long as its busiest SM sub-partition, so 4.1 warps per SM cost ~45 % more than 4.0
+    (profiles/README.md).  This picks the smallest S such that all segments -- including the extra
+    end-aligned one -- need at most k * n_sm * warps_per_sm warps for the smallest possible k."""
+    N = (L - cfg.ntaps + 1) // cfg.os
+    wave = n_sm * warps_per_sm                                        # warps per full wave
+
+    def warps(S):
+        nfull, rem = divmod(N, S)
+        w = -(-nfull * nmodes // streams_per_warp)
+        return w + (-(-nmodes // streams_per_warp) if rem and nfull else 0)   # + the end-aligned extra launch
+
+    S = min(target, N)
+    k0 = warps(S) // wave                   # whole waves at the target length
+    if k0 == 0:
+        return S                            # less than one wave: nothing to balance
+    while S < N and warps(S) > k0 * wave:   # grow S (by at most a factor 1 + 1/k0) to drop the partial wave
+        S += 1
+    return S
+
+
 def shard_segments(nseg, rank, world):
     """Contiguous block of segment indices owned by ``rank`` (no exchange between ranks)."""
     base, extra = divmod(nseg, world)
@@ -110,6 +134,7 @@ class SegmentedReceiver:
         self.bps_tables = device.BpsTables(cfg.bps_angles, alphabet, self.cdtype.type, self.dev)
         self.w0 = torch.from_numpy(theory.init_taps(cfg.ntaps, nmodes, self.cdtype.type)).to(self.dev)
         self.side = None
+        self._streams = None
         self.events = None      # set to a list to collect (name, (start, end)) CUDA events per launch
         self.want_idx = True
 
@@ -178,6 +203,76 @@ class SegmentedReceiver:
         if len(groups) > 1:
             main.wait_stream(self.side)
         return res
+
+
+def _host_chunks(groups, nchunks):
+    """Split the main group into ``nchunks`` runs of whole segments; the end-aligned extra segment (if
+    any) becomes the last chunk.  Yields (first_symbol, nsym, nseg, drop, seg_index0)."""
+    first, nsym, nseg, drop = groups[0]
+    nchunks = max(1, min(nchunks, nseg))
+    for c in range(nchunks):
+        lo, hi = shard_segments(nseg, c, nchunks)
+        if hi > lo:
+            yield first + lo * nsym, nsym, hi - lo, 0, lo
+    if len(groups) > 1:
+        f2, n2, k2, d2 = groups[1]
+        yield f2, n2, k2, d2, nseg
+
+
+def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None):
+    """End-to-end form of :meth:`SegmentedReceiver.run` for a capture in (pinned) HOST memory.
+
+    The capture is cut into ``nchunks`` runs of whole segments; the H2D copy of chunk c+1, the chain of
+    chunk c (on its own stream) and the D2H copy of the recovered symbols + phases of chunk c-1 overlap,
+    so the wall time approaches max(copy in, compute, copy out) instead of their sum.  Results land in
+    ``out_host`` / ``ph_host`` with shape (nseg_total, nmodes, S) (segment major, like the device
+    layout; the last row is the end-aligned extra segment when S does not divide the capture).
+    Returns (out_host, ph_host, groups)."""
+    cfg = rx.cfg
+    nmodes, L = E_host.shape
+    groups = plan_segments(L, cfg)
+    nseg_total = sum(g[2] for g in groups)
+    S = groups[0][1]
+    if out_host is None:
+        out_host = torch.empty((nseg_total, nmodes, S), dtype=rx.tdtype, pin_memory=True)
+    if ph_host is None:
+        ph_host = torch.empty((nseg_total, nmodes, S), dtype=rx.rdtype, pin_memory=True)
+    if E_dev is None:
+        E_dev = torch.empty((nmodes, L), dtype=rx.tdtype, device=rx.dev)
+    if rx._streams is None:
+        rx._streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
+                           comp=[torch.cuda.Stream() for _ in range(4)])
+    st = rx._streams
+    main = torch.cuda.current_stream()
+    for s_ in [st["h2d"], st["d2h"]] + st["comp"]:
+        s_.wait_stream(main)
+    events, rx.events = rx.events, None
+    keep = []
+    copied_to = 0                                                   # samples [0, copied_to) are on the device
+    for ci, (first, nsym, nseg, drop, seg0) in enumerate(_host_chunks(groups, nchunks)):
+        need = min(L, (first + nsym * nseg) * cfg.os + cfg.ntaps - 1)
+        ev_in = torch.cuda.Event()
+        with torch.cuda.stream(st["h2d"]):
+            if need > copied_to:
+                E_dev[:, copied_to:need].copy_(E_host[:, copied_to:need], non_blocking=True)
+                copied_to = need
+            ev_in.record()
+        comp = st["comp"][ci % len(st["comp"])]
+        ev_out = torch.cuda.Event()
+        with torch.cuda.stream(comp):
+            comp.wait_event(ev_in)
+            res = rx._run_group(E_dev, first, nsym, nseg, drop, None, None)
+            ev_out.record()
+        with torch.cuda.stream(st["d2h"]):
+            st["d2h"].wait_event(ev_out)
+            out_host[seg0:seg0 + nseg].copy_(res["out"], non_blocking=True)
+            ph_host[seg0:seg0 + nseg].copy_(res["ph"], non_blocking=True)
+        keep.append(res)
+    for s_ in [st["h2d"], st["d2h"]] + st["comp"]:
+        main.wait_stream(s_)
+    rx.events = events
+    rx._keep = keep                                                 # alive until the caller synchronises
+    return out_host, ph_host, groups
 
 
 def stitch(groups, key):

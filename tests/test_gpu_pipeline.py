@@ -38,10 +38,9 @@ def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypa
     if kernel == "warp":
         monkeypatch.setenv("QB_TRAIN_KERNEL", "warp")
     elif kernel == "la8":
-        pass                                          # default: 8 lanes per stream, look-ahead form
+        monkeypatch.setenv("QB_TRAIN_LA", "1")        # opt-in look-ahead form (8 lanes, ntaps 21/45 shapes)
     else:
-        monkeypatch.setenv("QB_TRAIN_LA", "0")        # direct form of the recurrence
-        monkeypatch.setenv("QB_TRAIN_LPS", kernel[3:])
+        monkeypatch.setenv("QB_TRAIN_LPS", kernel[3:])  # default direct form of the recurrence
     E, _ = env.synth.synth_numpy(M, 5000, nmodes=nmodes, seed=M + ntaps, snr_db=24.0)
     t = env.torch
     nseg, S = 3, 1500
