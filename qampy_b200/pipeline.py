@@ -239,9 +239,11 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None):
         ph_host = torch.empty((nseg_total, nmodes, S), dtype=rx.rdtype, pin_memory=True)
     if E_dev is None:
         E_dev = torch.empty((nmodes, L), dtype=rx.tdtype, device=rx.dev)
-    if rx._streams is None:
+    if rx._streams is None or len(rx._streams["comp"]) < min(nchunks + 1, 17):
+        # one compute stream per chunk: the training kernel is latency bound, so the chains of different
+        # chunks must run side by side rather than queue behind each other
         rx._streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
-                           comp=[torch.cuda.Stream() for _ in range(4)])
+                           comp=[torch.cuda.Stream() for _ in range(min(nchunks + 1, 17))])
     st = rx._streams
     main = torch.cuda.current_stream()
     for s_ in [st["h2d"], st["d2h"]] + st["comp"]:
@@ -254,7 +256,8 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None):
         ev_in = torch.cuda.Event()
         with torch.cuda.stream(st["h2d"]):
             if need > copied_to:
-                E_dev[:, copied_to:need].copy_(E_host[:, copied_to:need], non_blocking=True)
+                for k in range(nmodes):          # row by row: contiguous slices -> plain async DMA
+                    E_dev[k, copied_to:need].copy_(E_host[k, copied_to:need], non_blocking=True)
                 copied_to = need
             ev_in.record()
         comp = st["comp"][ci % len(st["comp"])]
