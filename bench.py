@@ -258,9 +258,18 @@ def run_b200(a, rank, local_rank, world):
     per = {}
     for name, (s, e) in events:
         per.setdefault(name, []).append(s.elapsed_time(e))
-    # dominant kernel: eq_train.  One step launches it once per stage and segment group.
-    train_ms = sum(per.get("train", [0.0])) / a.steps
-    train_bytes = BYTES_TRAIN * nsym_out * len(cfg.methods)
+    # roofline of the dominant kernel = the stage with the largest device time per step.  Algorithmic
+    # bytes per symbol period: train 48 B per pass, apply 48 B, bps 40 B.
+    stage_ms = {k: sum(v) / a.steps for k, v in per.items()}
+    stage_bytes = {"train": BYTES_TRAIN * nsym_out * len(cfg.methods), "apply": BYTES_APPLY * nsym_out,
+                   "bps": BYTES_BPS * nsym_out}
+    stage_gbs = {k: stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 for k in stage_ms if stage_ms[k] > 0}
+    kernels = {"train": "train_sub_kernel<8,12,METHOD> (eq_train fast path; two launches per step: mcma, mrde)",
+               "apply": "apply_2x2_os2_kernel", "bps": "bps_kernel<float>"}
+    limits = {"train": "serial-recurrence latency + FP32 issue (60 flop/B at ntaps 45), not HBM",
+              "apply": "FP32 FMA issue (30 flop/B at ntaps 45), not HBM",
+              "bps": "FP32 issue of the 64-angle distance search + one serial FADD chain per angle, not HBM"}
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "train"
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -268,17 +277,17 @@ def run_b200(a, rank, local_rank, world):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = train_bytes / (train_ms * 1e-3) / 1e9 if train_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "train_sub_kernel (eq_train fast path, both stages)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "binding_limit": "serial recurrence latency / FP32 issue, not HBM (DESIGN.md)",
-                "stage_ms_per_step": {k: sum(v) / a.steps for k, v in per.items()},
-                "stage_gbs": {"train": achieved,
-                              "apply": BYTES_APPLY * nsym_out / (sum(per.get("apply", [0])) / a.steps * 1e-3) / 1e9
-                              if per.get("apply") else None,
-                              "bps": BYTES_BPS * nsym_out / (sum(per.get("bps", [0])) / a.steps * 1e-3) / 1e9
-                              if per.get("bps") else None}}
+    achieved = stage_gbs.get(dom, 0.0)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+    # workload (profiles/r01_ncu_full_summary.txt); algorithmic bytes per launch are stage_bytes / launches
+    traffic = {"train": 326.1e6, "apply": 450.7e6, "bps": 348.5e6}
+    roofline = {"bound": "hbm", "kernel": kernels[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic.get(dom) if a.nsym == 10 ** 7 else None,
+                "launches_per_step": {"train": len(cfg.methods), "apply": 1, "bps": 1}[dom],
+                "algorithmic_bytes_per_launch": stage_bytes[dom] / {"train": len(cfg.methods), "apply": 1, "bps": 1}[dom],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "binding_limit": limits[dom], "stage_ms_per_step": stage_ms, "stage_gbs": stage_gbs,
+                "stage_frac": {k: v / peak for k, v in stage_gbs.items()}}
 
     # end to end: pinned host capture -> H2D -> chain -> D2H of the recovered symbols + phase, with
     # the copies of neighbouring chunks overlapping the compute (pipeline.run_host)
