@@ -17,6 +17,8 @@
 // Arithmetic contract of the distance: unfused complex multiply, |z|^2 = fl(fl(re*re) +
 // fl(im*im)); for a full rectangular alphabet the per-axis slicer returns the same bits as the brute
 // force search because IEEE rounding is monotone.
+#include <stdlib.h>
+
 #include "qb_common.cuh"
 
 namespace qb {
@@ -298,6 +300,205 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised BPS kernel (default).  Same arithmetic as bps_kernel, but the parallel distance
+// search and the serial tail run CONCURRENTLY inside a CTA:
+//   producer warps (4)      distances of tile m+1 -> ring rows, one angle column per thread
+//   consumer warps (A/32)   running sums + window differences of tile m (thread = angle column), then
+//                           consumer warp 0: arg-min (16 rows x 2 angle halves), unwrap, phase output, rotation
+// hand-off by named barriers (bar.arrive / bar.sync): FULL[m&1] producers -> consumers, EMPTY[m&1] back.
+// A tile is 16 rows; the power-of-two ring holds >= 2N + 32 rows so the producers may run one tile
+// ahead of the consumers without touching a row a window difference still needs.
+// ------------------------------------------------------------------------------------------------
+constexpr int WS_TR = 16;
+constexpr int WS_PW = 4;   // producer warps
+
+// barrier ids are immediates so that the kernel reserves 6 named barriers, not all 16
+template <int ID>
+__device__ __forceinline__ void named_bar_sync(int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void named_bar_arrive(int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID0>
+__device__ __forceinline__ void named_bar_sync2(int parity, int count)
+{
+    if (parity) named_bar_sync<ID0 + 1>(count); else named_bar_sync<ID0>(count);
+}
+template <int ID0>
+__device__ __forceinline__ void named_bar_arrive2(int parity, int count)
+{
+    if (parity) named_bar_arrive<ID0 + 1>(count); else named_bar_arrive<ID0>(count);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * (WS_PW + 8)) bps_ws_kernel(BpsParams<T> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = p.A, W = 2 * p.N, N = p.N;
+    constexpr int TR = WS_TR, TRP = WS_TR + 1;
+    const int CW = (A + 31) >> 5;                     // consumer warps
+    const int NT = (int)blockDim.x;                   // 32 * (CW + WS_PW)
+    const int RMASK = p.ring_rows - 1;
+    const long long L = p.L;
+    const int Ah = (A + 1) >> 1;                      // first half of the angles (arg-min split)
+
+    cx<T> *comp = reinterpret_cast<cx<T> *>(smem_raw);  // [A]
+    cx<T> *syms = comp + A;
+    const bool slicer = p.n_re > 0;
+    const int npr = slicer ? max(p.n_re - 1, 1) : 0, npi = slicer ? max(p.n_im - 1, 1) : 0;
+    cx<T> *pre = syms, *pim = syms + npr;
+    T *ring = reinterpret_cast<T *>(syms + (slicer ? npr + npi : p.M));  // [RR][A]
+    T *dt = ring + (size_t)p.ring_rows * A;             // [A][TRP], upper angle half shifted by 16 banks
+    T *angs = dt + (size_t)A * TRP + 32;                // [A]
+
+    const cx<T> *E = p.E + (long long)blockIdx.x * p.stream_stride;
+    int32_t *idx = p.idx ? p.idx + (long long)blockIdx.x * L : nullptr;
+    T *ph = p.ph ? p.ph + (long long)blockIdx.x * L : nullptr;
+    cx<T> *Eout = p.Eout ? p.Eout + (long long)blockIdx.x * L : nullptr;
+
+    for (int c = tid; c < A; c += NT) {
+        comp[c] = p.comp[c];
+        angs[c] = p.angles ? p.angles[c] : (T)0;
+    }
+    AxisGrid<T> gre, gim;
+    gre.scale = gre.bias = gim.scale = gim.bias = (T)0;
+    gre.npair = gim.npair = 1;
+    if (slicer) {
+        for (int c = tid; c < npr; c += NT) pre[c] = make_cx<T>(p.lev_re[c], p.lev_re[min(c + 1, p.n_re - 1)]);
+        for (int c = tid; c < npi; c += NT) pim[c] = make_cx<T>(p.lev_im[c], p.lev_im[min(c + 1, p.n_im - 1)]);
+        gre = make_grid(p.lev_re, p.n_re);
+        gim = make_grid(p.lev_im, p.n_im);
+    } else {
+        for (int c = tid; c < p.M; c += NT) syms[c] = p.symbols[c];
+    }
+    // edges: idx = 0 -> ph = angles[0], not unwrapped (phaserecovery.py:155 touches [N:-N] only)
+    const long long lo = N < L ? N : L;
+    const long long hi = (L - N > lo) ? L - N : lo;
+    __syncthreads();
+    {
+        const T a0 = angs[0];
+        const long long nedge = lo + (L - hi);
+        for (long long c = tid; c < nedge; c += NT) {
+            const long long j = c < lo ? c : hi + (c - lo);
+            if (idx) idx[j] = 0;
+            if (ph) ph[j] = a0;
+            if (Eout) Eout[j] = rotate<T>(E[j], a0);
+        }
+    }
+    const long long ntiles = (L + TR - 1) / TR;
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_CONS = 5;
+
+    if (warp >= CW) {
+        // =========================== producers: distance search ===================================
+        const int pt = tid - 32 * CW, NP = 32 * WS_PW;
+        const bool fixed = (NP % A) == 0;
+        const int my_a = pt % A, my_r0 = pt / A, rstep = fixed ? NP / A : 1;
+        const cx<T> my_c = comp[my_a];
+        for (long long m = 0; m < ntiles; m++) {
+            const long long i0 = m * TR;
+            const int nrows = (int)min((long long)TR, L - i0);
+            const int slot0 = (int)(i0 & RMASK);
+            if (m >= 2) named_bar_sync2<BAR_EMPTY>((int)(m & 1), NT);   // tile m-2 consumed: ring rows free
+            if (fixed) {
+                T *dst = ring + (size_t)slot0 * A + my_a;
+#pragma unroll 4
+                for (int r = my_r0; r < nrows; r += rstep)
+                    dst[r * A] = min_distance<T>(E[i0 + r], my_c, slicer, pre, pim, gre, gim, syms, p.M);
+            } else {
+                for (int f = pt; f < nrows * A; f += NP) {
+                    const int r = f / A, a = f - r * A;
+                    ring[(size_t)(slot0 + r) * A + a] =
+                        min_distance<T>(E[i0 + r], comp[a], slicer, pre, pim, gre, gim, syms, p.M);
+                }
+            }
+            named_bar_arrive2<BAR_FULL>((int)(m & 1), NT);
+        }
+    } else {
+        // =========================== consumers: serial tail ========================================
+        T csum = 0;                 // running column sum of angle column `tid` (tid < A)
+        T cum = 0, p4prev = 0;      // unwrap state (consumer warp 0)
+        const int NC = 32 * CW;
+        for (long long m = 0; m < ntiles; m++) {
+            const long long i0 = m * TR;
+            const int nrows = (int)min((long long)TR, L - i0);
+            const int slot0 = (int)(i0 & RMASK);
+            named_bar_sync2<BAR_FULL>((int)(m & 1), NT);
+            if (tid < A) {
+                T *xp = ring + (size_t)slot0 * A + tid;
+                T *dp = dt + (size_t)tid * TRP + (tid >= Ah ? 16 : 0);
+#pragma unroll 4
+                for (int r = 0; r < nrows; r++) {
+                    const T old = ring[(size_t)((slot0 + r - W) & RMASK) * A + tid];   // csum[i-W]; unused if i < W
+                    csum = (i0 + r == 0) ? (T)0 : add_rn(csum, xp[r * A]);             // row 0 is never added (:30)
+                    xp[r * A] = csum;
+                    dp[r] = sub_rn(csum, old);
+                }
+            }
+            named_bar_arrive2<BAR_EMPTY>((int)(m & 1), NT);     // ring rows of this tile are final
+            named_bar_sync<BAR_CONS>(NC);                        // dt complete
+            if (warp == 0) {
+                const int r = lane & 15, h = lane >> 4;
+                const long long i = i0 + r, j = i - N;
+                const bool valid = r < nrows && i >= W && h == 0;
+                const int a0 = h ? Ah : 0, a1 = h ? A : Ah;
+                T best = (T)1000.;
+                int bk = 0x7fffffff;
+                const T *dr = dt + r + (h ? 16 : 0);
+#pragma unroll 8
+                for (int a = a0; a < a1; a++) {
+                    const T v = dr[a * TRP];
+                    if (v < best) {   // strict: first minimum, dmin0 = 1000 (:31, :39)
+                        best = v;
+                        bk = a;
+                    }
+                }
+                {   // lower half wins ties (smaller angle index)
+                    const T ob = shfl_xor(best, 16);
+                    const int ok = shfl_xor(bk, 16);
+                    if (ob < best || (ob == best && ok < bk)) {
+                        best = ob;
+                        bk = ok;
+                    }
+                }
+                if (bk == 0x7fffffff) bk = 0;
+                named_bar_sync<BAR_CONS>(NC);                    // dt may be rewritten by the next phase 2
+                if (idx && valid) idx[j] = bk;
+                if (ph) {
+                    const T p4 = mul_rn(angs[bk], (T)4);
+                    T pp = __shfl_up_sync(0xffffffffu, p4, 1);
+                    if (r == 0) pp = p4prev;
+                    T corr = (T)0;
+                    if (valid && j > N) corr = unwrap_corr<T>(p4, pp);
+                    unsigned mask = __ballot_sync(0xffffffffu, corr != (T)0);
+                    T mycum = cum;
+                    while (mask) {   // fold the (rare) non-zero corrections in row order: exact sequential sum
+                        const int e = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const T ce = shfl_idx(corr, e);
+                        cum = add_rn(cum, ce);
+                        if (lane >= e) mycum = cum;
+                    }
+                    const T phv = add_rn(p4, mycum) / (T)4;
+                    if (valid) {
+                        ph[j] = phv;
+                        if (Eout) Eout[j] = rotate<T>(E[j], phv);
+                    }
+                    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                    if (vm) p4prev = shfl_idx(p4, 31 - __clz(vm));
+                }
+            } else {
+                named_bar_sync<BAR_CONS>(NC);
+            }
+        }
+    }
+}
+
 template <typename T>
 static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
                       const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
@@ -335,9 +536,28 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     if (!attr_done[sizeof(T) == 8]) {
         QB_CUDA_CHECK(cudaFuncSetAttribute(bps_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            200 * 1024));
+        QB_CUDA_CHECK(cudaFuncSetAttribute(bps_ws_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
         attr_done[sizeof(T) == 8] = true;
     }
     if (nstream > 2147483647LL) return set_error(QB_ERR_UNSUPPORTED, "bps: too many streams");
+    // default: warp-specialised kernel; QB_BPS_KERNEL=simple selects the phase-by-phase one (tests run both)
+    const char *force = getenv("QB_BPS_KERNEL");
+    if (!(force && force[0] == 's')) {
+        int RRw = 64;
+        while (RRw < 2 * WS_TR + W) RRw <<= 1;
+        const size_t smem_ws = ((size_t)RRw * A + (size_t)A * (WS_TR + 1) + 32 + A) * sizeof(T) +
+                               (A + (n_re ? n_re + n_im : M)) * sizeof(cx<T>) + 64;
+        if (smem_ws <= 200 * 1024) {
+            p.tile_rows = WS_TR;
+            p.ring_rows = RRw;
+            const int threads = 32 * (WS_PW + (int)((A + 31) / 32));
+            bps_ws_kernel<T><<<(unsigned)nstream, threads, smem_ws, st>>>(p);
+            count_launch();
+            QB_CUDA_CHECK(cudaGetLastError());
+            return QB_OK;
+        }
+    }
     bps_kernel<T><<<(unsigned)nstream, BPS_THREADS, smem, st>>>(p);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());

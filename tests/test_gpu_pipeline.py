@@ -129,8 +129,19 @@ def test_apply_batched_generic_and_fast(env):
     assert rms(out.cpu().numpy() - env.co.apply_segments(E[None], 2, w)) < 1e-13
 
 
-@pytest.mark.parametrize("M,A,N", [(32, 32, 11), (64, 64, 45), (4, 16, 5), (128, 48, 20), (256, 64, 32)])
-def test_bps_slicer_and_bruteforce_vs_oracle(env, M, A, N):
+@pytest.fixture(params=["ws", "simple"])
+def bps_kernel(request, monkeypatch):
+    """Both BPS kernels: warp-specialised (default) and phase-by-phase."""
+    if request.param == "simple":
+        monkeypatch.setenv("QB_BPS_KERNEL", "simple")
+    else:
+        monkeypatch.delenv("QB_BPS_KERNEL", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("M,A,N", [(32, 32, 11), (64, 64, 45), (4, 16, 5), (128, 48, 20), (256, 64, 32),
+                                   (16, 100, 70)])
+def test_bps_slicer_and_bruteforce_vs_oracle(env, bps_kernel, M, A, N):
     """Cross constellations (32/128) have no rectangular grid -> brute force; square ones use the
     slicer, which must give the same bits as brute force and as the oracle."""
     t = env.torch
@@ -155,13 +166,13 @@ def test_bps_slicer_and_bruteforce_vs_oracle(env, M, A, N):
         assert rms(out[r].cpu().numpy() - Eb) < 1e-6
 
 
-def test_bps_edge_lengths(env):
+def test_bps_edge_lengths(env, bps_kernel):
     """L <= 2N (no interior), L = 2N + 1, L = 1, empty."""
     t = env.torch
     alphabet = env.theory.normalised_symbols(16).astype(np.complex64)
     tables = env.device.BpsTables(32, alphabet, np.complex64, env.dev)
     rng = np.random.default_rng(1)
-    for L in (1, 7, 20, 21, 22, 64, 65):
+    for L in (1, 7, 15, 16, 17, 20, 21, 22, 31, 32, 33, 64, 65, 1000):
         x = (alphabet[rng.integers(0, 16, (1, L))] * np.exp(0.2j)).astype(np.complex64)
         out, ph, idx = env.device.bps(t.from_numpy(x).to(env.dev), tables, 10)
         Eb, phr = env.co.bps_driver(x[0], 32, alphabet, 10)
