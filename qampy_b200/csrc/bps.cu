@@ -499,6 +499,12 @@ __global__ void __launch_bounds__(32 * (WS_PW + 8)) bps_ws_kernel(BpsParams<T> p
     }
 }
 
+// bps_fast.cu: column-per-lane kernel (complex64, rectangular alphabet, A in {32,64,96,128});
+// returns 1 when the problem is not covered.
+int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int64_t L, const void *comp,
+                      const void *angles, int64_t A, const void *lev_re, int64_t n_re, const void *lev_im,
+                      int64_t n_im, int64_t N, int32_t *idx, void *ph, void *Eout, cudaStream_t st);
+
 template <typename T>
 static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
                       const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
@@ -541,8 +547,14 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
         attr_done[sizeof(T) == 8] = true;
     }
     if (nstream > 2147483647LL) return set_error(QB_ERR_UNSUPPORTED, "bps: too many streams");
-    // default: warp-specialised kernel; QB_BPS_KERNEL=simple selects the phase-by-phase one (tests run both)
+    // default: column-per-lane kernel (bps_fast.cu) where it applies, else the warp-specialised tile kernel;
+    // QB_BPS_KERNEL=ws / simple select the tile kernels (tests run all three)
     const char *force = getenv("QB_BPS_KERNEL");
+    if (sizeof(T) == 4 && !(force && (force[0] == 's' || force[0] == 'w'))) {
+        const int rc = bps_fast_dispatch(E, nstream, stream_stride, L, comp, angles, A, lev_re, n_re, lev_im, n_im,
+                                         N, idx, ph, Eout, st);
+        if (rc <= 0) return rc;
+    }
     if (!(force && force[0] == 's')) {
         int RRw = 64;
         while (RRw < 2 * WS_TR + W) RRw <<= 1;

@@ -1,0 +1,411 @@
+// bps_fast: column-per-lane blind phase search (complex64, rectangular alphabet, A in {32,64,96,128}).
+//
+// Same function as bps_kernel in bps.cu (bps + select_angle_index + select_angles,
+// qampy/core/pythran_dsp.py:47-85, 26-42, 137-153, and the L2 tail qampy/core/phaserecovery.py:150-159)
+// and the same arithmetic contract: unfused complex multiply, d = fl(fl(dr^2)+fl(di^2)),
+// clamp at 100, running column sum added in the reference's order, window difference, first strict
+// arg-min with dmin0 = 1000.  What changes is the mapping, chosen to minimise issued instructions,
+// which is what bounds this kernel (1.28e9 distance evaluations at C3, ~0.4 kB of HBM traffic each 1000):
+//
+//   * one lane owns one test-angle COLUMN of one stream for the whole stream: its rotation constants,
+//     its running sum and its place in the ring live in registers; a warp owns 32 columns, a CTA of
+//     A/32 warps owns one stream.  The distance, the running sum and the window difference of a
+//     (row, angle) pair never leave the lane -- no distance matrix in shared memory, no phase barriers.
+//   * the history csum[i-2N] is a ring of EXACTLY 2N rows per warp (one LDS + one STS at the same
+//     address per row), 11.5 kB per warp at N = 45, so 16 warps are resident per SM.
+//   * the arg-min over the angles is ONE warp reduction per row: window differences are non-negative
+//     floats, so their bit patterns order like unsigned integers and CREDUX.MIN (redux.sync.min.u32)
+//     gives the minimum; the first lane holding it comes from a ballot.  Rows are recorded as
+//     (min bits, ballot) and turned into an index 32 rows at a time (lane = row) in the tail.
+//   * packed fp32 (FMUL2 / FADD2, Blackwell) halves the issue slots of the rotation, the two level
+//     differences per axis and the squares; the slicer coordinate is one FFMA.SAT (clamp for free) plus
+//     one FFMA that leaves the bracket index in the low mantissa bits.  ptxas contracts
+//     mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both carry .rn, so every addition that
+//     consumes a packed product is a scalar add.rn (checked in SASS: the kernel contains no FFMA2).
+//   * the tail (arg-min combine across warps, unwrap, phase output, rotation) runs once per 32 rows
+//     with lane = row, on the warps of the CTA in turn so that none of them falls behind.
+#include <stdlib.h>
+
+#include "qb_common.cuh"
+
+namespace qb {
+
+struct BpsFastParams {
+    const float2 *E;
+    const float2 *comp;
+    const float *angles;
+    const float *lev_re, *lev_im;
+    int32_t *idx;
+    float *ph;
+    float2 *Eout;
+    long long stream_stride, L;
+    int A, n_re, n_im, N;
+};
+
+// (s*v.x, s*v.y), each product rounded once (FMUL2 with a broadcast scalar operand)
+__device__ __forceinline__ float2 mul2_bcast(float s, float2 v)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "mul.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(s), "f"(v.x), "f"(v.y));
+    return r;
+}
+// (s+v.x, s+v.y)  (FADD2).  Never feed it a packed product: ptxas would contract the pair into FFMA2.
+__device__ __forceinline__ float2 add2_bcast(float s, float2 v)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "add.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(s), "f"(v.x), "f"(v.y));
+    return r;
+}
+// (a.x*a.x, a.y*a.y)
+__device__ __forceinline__ float2 sqr2(float2 a)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mul.rn.f32x2 rc, ra, ra;\n\t"
+        "mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
+{
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr)
+{
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
+
+// Slicer constants of one axis.  The table entry f holds the NEGATED bracket (-lev[f], -lev[min(f+1, n-1)]),
+// f = 0 .. n-1, so that the two candidate differences are one FADD2.  f = floor((t - lev0)/step) clamped to
+// [0, n-1] is computed as u = sat(t*s1 + b1) (u = (x - 1/2)/(n-1) clamped to [0, 1]) followed by
+// w = u*(n-1) + 1.5*2^23, whose low mantissa bits are round(x - 1/2).  A coordinate that lands on the
+// wrong side of an integer by rounding still selects a bracket with the nearest level as an end point,
+// and the differences use the stored level values, so the minimum is bit-identical to the reference's
+// search over all M symbols (IEEE rounding is monotone).
+struct FastAxis {
+    float s1, b1, nm1;
+    uint32_t kaddr;   // table byte address - (0x4b400000 << 3)
+};
+__device__ __forceinline__ FastAxis make_fast_axis(const float *lev, int n, uint32_t tab_addr)
+{
+    FastAxis g;
+    const float span = n > 1 ? lev[n - 1] - lev[0] : 1.f;
+    const float step = n > 1 ? span / (float)(n - 1) : 1.f;
+    g.nm1 = (float)(n > 1 ? n - 1 : 0);
+    g.s1 = n > 1 ? 1.f / span : 0.f;
+    g.b1 = n > 1 ? (-lev[0] / step - 0.5f) / (float)(n - 1) : 0.f;
+    g.kaddr = tab_addr - (0x4b400000u << 3);
+    return g;
+}
+// min over the levels of |t - lev| (bit-exact), one axis
+__device__ __forceinline__ float axis_min_fast(float t, const FastAxis &g)
+{
+    const float u = fma_sat(t, g.s1, g.b1);
+    const float w = fmaf(u, g.nm1, 12582912.f);
+    const float2 nl = lds_f2((__float_as_uint(w) << 3) + g.kaddr);
+    const float2 df = add2_bcast(t, nl);
+    return fminf(fabsf(df.x), fabsf(df.y));
+}
+
+__device__ __forceinline__ float unwrap_corr_f(float p, float pprev)
+{
+    // one step of np.unwrap (default period / discont) in float32, op by op
+    const float PI = 3.14159274101257324219f, TWO_PI = 6.28318548202514648438f;
+    const float dd = __fsub_rn(p, pprev);
+    float m = fmodf(__fadd_rn(dd, PI), TWO_PI);
+    if (m != 0.f && m < 0.f) m = __fadd_rn(m, TWO_PI);
+    float ddmod = __fsub_rn(m, PI);
+    if (ddmod == -PI && dd > 0.f) ddmod = PI;
+    float corr = __fsub_rn(ddmod, dd);
+    if (fabsf(dd) < PI) corr = 0.f;
+    return corr;
+}
+__device__ __forceinline__ float2 rotate_f(float2 e, float ph)
+{
+    float s, c;
+    sincosf(ph, &s, &c);
+    return make_float2(e.x * c - e.y * s, e.x * s + e.y * c);
+}
+
+constexpr int FAST_TR = 32;   // rows per tile (= lanes of the tail)
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = 32 * NW;
+    const int N = p.N, W = 2 * p.N;
+    const long long L = p.L;
+    const unsigned FULL = 0xffffffffu;
+
+    // ---- shared memory ---------------------------------------------------------------------------
+    float2 *tabre = reinterpret_cast<float2 *>(smem_raw);                 // [n_re]
+    float2 *tabim = tabre + p.n_re;                                        // [n_im]
+    float2 *stage = tabim + p.n_im;                                        // [NW][32] input rows of the tile
+    uint2 *part = reinterpret_cast<uint2 *>(stage + NW * FAST_TR);         // [2][NW][32] hand-over to the tail
+    float *angs = reinterpret_cast<float *>(part + 2 * NW * FAST_TR);      // [A]
+    float *ust = angs + p.A;                                               // [2] unwrap state (cum, p4prev)
+    float *ring = ust + 2;                                                 // [NW][W][32] running sums
+
+    const float2 *E = p.E + (long long)blockIdx.x * p.stream_stride;
+    int32_t *idx = p.idx ? p.idx + (long long)blockIdx.x * L : nullptr;
+    float *ph = p.ph ? p.ph + (long long)blockIdx.x * L : nullptr;
+    float2 *Eout = p.Eout ? p.Eout + (long long)blockIdx.x * L : nullptr;
+
+    for (int c = tid; c < p.n_re; c += NT)
+        tabre[c] = make_float2(-p.lev_re[c], -p.lev_re[min(c + 1, p.n_re - 1)]);
+    for (int c = tid; c < p.n_im; c += NT)
+        tabim[c] = make_float2(-p.lev_im[c], -p.lev_im[min(c + 1, p.n_im - 1)]);
+    for (int c = tid; c < p.A; c += NT) angs[c] = p.angles ? p.angles[c] : 0.f;
+    float *ring_w = ring + (size_t)warp * W * 32;
+    for (int c = lane; c < W * 32; c += 32) ring_w[c] = 0.f;   // slot 0 = csum[0] = 0 (pythran_dsp.py:28)
+    FastAxis gre = make_fast_axis(p.lev_re, p.n_re, smem_u32(tabre));
+    FastAxis gim = make_fast_axis(p.lev_im, p.n_im, smem_u32(tabim));
+    // bounce the address constants through shared memory: ptxas otherwise splits (bits(w) << 3) + kaddr
+    // into LEA + IADD of the two halves of kaddr, one more instruction per axis and evaluation
+    if (tid == 0) {
+        reinterpret_cast<uint32_t *>(ust)[0] = gre.kaddr;
+        reinterpret_cast<uint32_t *>(ust)[1] = gim.kaddr;
+    }
+    __syncthreads();
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gre.kaddr) : "r"(smem_u32(ust)));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(gim.kaddr) : "r"(smem_u32(ust)));
+    __syncthreads();
+    if (tid < 2) ust[tid] = 0.f;
+    __syncthreads();
+
+    // edges: idx = 0 -> ph = angles[0], not unwrapped (phaserecovery.py:155 touches [N:-N] only)
+    const long long lo = N < L ? N : L;
+    const long long hi = (L - N > lo) ? L - N : lo;
+    {
+        const float a0 = angs[0];
+        const long long nedge = lo + (L - hi);
+        for (long long c = tid; c < nedge; c += NT) {
+            const long long j = c < lo ? c : hi + (c - lo);
+            if (idx) idx[j] = 0;
+            if (ph) ph[j] = a0;
+            if (Eout) Eout[j] = rotate_f(E[j], a0);
+        }
+    }
+
+    // ---- this lane's angle column ------------------------------------------------------------------
+    const float2 cc = p.comp[warp * 32 + lane];
+    const float2 c1 = make_float2(cc.x, cc.y);      // e.x * (cr,  ci)
+    const float2 c2 = make_float2(-cc.y, cc.x);     // e.y * (-ci, cr)   (negation commutes with rounding)
+    float csum = 0.f;
+    const uint32_t ring_lo = smem_u32(ring_w) + 4u * lane;
+    const uint32_t stage_addr = smem_u32(stage + warp * FAST_TR);
+    float cum = 0.f, p4prev = 0.f;                  // unwrap state (NW == 1: registers; else via ust[])
+
+    const long long ntiles = (L + FAST_TR - 1) / FAST_TR;
+    float2 enext = lane < L ? E[lane] : make_float2(0.f, 0.f);
+    uint2 mine = make_uint2(0xffffffffu, 0u);       // (min bits, ballot) of tile row `lane`
+
+    // Four consecutive rows of this lane's column: distance -> running sum -> window difference -> warp
+    // arg-min record.  The four distance evaluations are independent (ILP); only the running sum chains.
+    // Rows 0,1 of the group sit at ring address aA (+128), rows 2,3 at aB (+128): the ring has an even
+    // number of rows and groups start at even slots, so a pair never straddles the wrap.  Shared-memory
+    // accesses are volatile asm in exactly the order wanted: 4 input rows, 4 old sums, 4 new sums.
+    auto group = [&](bool first, int rbase, uint32_t aA, uint32_t aB) {
+        float2 e[4];
+        float old[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[u].x), "=f"(e[u].y)
+                         : "r"(stage_addr + 8u * (rbase + u)));
+        // csum[i - 2N] (0 while i < 2N: unused)
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[0]) : "r"(aA));
+        asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[1]) : "r"(aA));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[2]) : "r"(aB));
+        asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[3]) : "r"(aB));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float2 pa = mul2_bcast(e[u].x, c1), pb = mul2_bcast(e[u].y, c2);
+            const float tr = __fadd_rn(pa.x, pb.x);     // E[i]*comp[a], unfused (pythran_dsp.py:79)
+            const float ti = __fadd_rn(pa.y, pb.y);
+            float2 dm;
+            dm.x = axis_min_fast(tr, gre);
+            dm.y = axis_min_fast(ti, gim);
+            const float2 sq = sqr2(dm);
+            c[u] = fminf(__fadd_rn(sq.x, sq.y), 100.f);                 // :73, :81-82 (NaN -> 100)
+        }
+        if (first) c[0] = 0.f;                                          // row 0 is never added (:30)
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            csum = __fadd_rn(csum, c[u]);                               // :33/:36, sequential
+            c[u] = csum;
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aA), "f"(c[0]));
+        asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(aA), "f"(c[1]));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aB), "f"(c[2]));
+        asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(aB), "f"(c[3]));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned db = __float_as_uint(__fsub_rn(c[u], old[u]));   // >= +0: orders like an unsigned
+            const unsigned mn = __reduce_min_sync(FULL, db);
+            const unsigned bal = __ballot_sync(FULL, db == mn);
+            if (lane == rbase + u) mine = make_uint2(mn, bal);
+        }
+    };
+
+    int slot = 0;   // ring slot (= row index mod 2N) of the next group's first row; always even
+    for (long long m = 0; m < ntiles; m++) {
+        const long long i0 = m * FAST_TR;
+        const int nrows = (int)min((long long)FAST_TR, L - i0);
+        __syncwarp();
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_addr + 8u * lane), "f"(enext.x), "f"(enext.y)
+                     : "memory");
+        __syncwarp();
+        if (i0 + FAST_TR + lane < L) enext = E[i0 + FAST_TR + lane];
+
+        // rows past the end of the stream (last group only) run on stale inputs: they come after every
+        // valid row in the running sums and are masked in the tail
+        const int ngroups = (nrows + 3) >> 2;
+#pragma unroll 1
+        for (int g = 0; g < ngroups; g++) {
+            const uint32_t aA = ring_lo + 128u * (uint32_t)slot;
+            if (slot + 4 <= W) {
+                group(m == 0 && g == 0, 4 * g, aA, aA + 256u);
+                slot += 4;
+                if (slot == W) slot = 0;
+            } else {                                   // slot == W - 2: rows 2,3 wrap to slots 0,1
+                group(m == 0 && g == 0, 4 * g, aA, ring_lo);
+                slot = 2;
+            }
+        }
+        __syncwarp();
+
+        // ---- hand the 32 row records to the tail owner ----------------------------------------------
+        const int owner = (int)(m % NW);
+        uint2 *pbuf = part + (size_t)(m & 1) * NW * FAST_TR;
+        if (NW > 1) {
+            if (warp != owner) pbuf[warp * FAST_TR + lane] = mine;
+            __syncthreads();
+        }
+        if (warp == owner) {
+            // tail, lane = row: row i = i0 + lane with i >= 2N produces output j = i - N
+            unsigned best = 0xffffffffu, bb = 1u;
+            int bw = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {   // ascending angle blocks, strict <: first minimum (:39)
+                const uint2 q = (w == owner || NW == 1) ? mine : pbuf[w * FAST_TR + lane];
+                if (q.x < best) {
+                    best = q.x;
+                    bb = q.y;
+                    bw = w;
+                }
+            }
+            int bk = 32 * bw + __ffs(bb) - 1;
+            const long long i = i0 + lane, j = i - N;
+            const bool valid = lane < nrows && i >= W;
+            if (best >= 0x447a0000u || !valid) bk = 0;   // dmin0 = 1000 (:31): nothing below it -> idx stays 0
+            if (idx && valid) idx[j] = bk;
+            if (ph) {
+                if (NW > 1) {
+                    cum = ust[0];
+                    p4prev = ust[1];
+                }
+                const float p4 = __fmul_rn(angs[bk], 4.f);
+                float pp = __shfl_up_sync(FULL, p4, 1);
+                if (lane == 0) pp = p4prev;
+                float corr = 0.f;
+                if (valid && j > N) corr = unwrap_corr_f(p4, pp);
+                unsigned mask = __ballot_sync(FULL, corr != 0.f);
+                float mycum = cum;
+                while (mask) {   // fold the (rare) non-zero corrections in row order: exact sequential sum
+                    const int e = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float ce = __shfl_sync(FULL, corr, e);
+                    cum = __fadd_rn(cum, ce);
+                    if (lane >= e) mycum = cum;
+                }
+                const float phv = __fadd_rn(p4, mycum) / 4.f;
+                if (valid) {
+                    ph[j] = phv;
+                    if (Eout) Eout[j] = rotate_f(E[j], phv);
+                }
+                const unsigned vm = __ballot_sync(FULL, valid);
+                if (vm) p4prev = __shfl_sync(FULL, p4, 31 - __clz(vm));
+                if (NW > 1 && lane == 0) {
+                    ust[0] = cum;
+                    ust[1] = p4prev;
+                }
+            }
+        }
+    }
+}
+
+static size_t fast_smem_bytes(int NW, int A, int n_re, int n_im, int N)
+{
+    return (size_t)(n_re + n_im) * 8 + (size_t)NW * FAST_TR * 8 * 3 + (size_t)A * 4 + 8 +
+           (size_t)NW * 2 * N * 32 * 4;
+}
+
+template <int NW>
+static int launch_fast(const BpsFastParams &p, int64_t nstream, size_t smem, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        QB_CUDA_CHECK(cudaFuncSetAttribute(bps_fast_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+        attr_done = true;
+    }
+    bps_fast_kernel<NW><<<(unsigned)nstream, 32 * NW, smem, st>>>(p);
+    count_launch();
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+// Returns QB_OK after launching, or 1 if this problem is not covered by the fast kernel (caller falls
+// back to bps_kernel), or a negative error code.
+int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int64_t L, const void *comp,
+                      const void *angles, int64_t A, const void *lev_re, int64_t n_re, const void *lev_im,
+                      int64_t n_im, int64_t N, int32_t *idx, void *ph, void *Eout, cudaStream_t st)
+{
+    if (n_re < 1 || n_im < 1 || A % 32 != 0 || A > 128 || N < 2) return 1;   // ring needs >= 4 rows
+    const int NW = (int)(A / 32);
+    const size_t smem = fast_smem_bytes(NW, (int)A, (int)n_re, (int)n_im, (int)N);
+    if (smem > 100 * 1024) return 1;
+    BpsFastParams p;
+    p.E = (const float2 *)E;
+    p.comp = (const float2 *)comp;
+    p.angles = (const float *)angles;
+    p.lev_re = (const float *)lev_re;
+    p.lev_im = (const float *)lev_im;
+    p.idx = idx;
+    p.ph = (float *)ph;
+    p.Eout = (float2 *)Eout;
+    p.stream_stride = stream_stride;
+    p.L = L;
+    p.A = (int)A;
+    p.n_re = (int)n_re;
+    p.n_im = (int)n_im;
+    p.N = (int)N;
+    switch (NW) {
+    case 1: return launch_fast<1>(p, nstream, smem, st);
+    case 2: return launch_fast<2>(p, nstream, smem, st);
+    case 3: return launch_fast<3>(p, nstream, smem, st);
+    default: return launch_fast<4>(p, nstream, smem, st);
+    }
+}
+
+}  // namespace qb

@@ -129,18 +129,20 @@ def test_apply_batched_generic_and_fast(env):
     assert rms(out.cpu().numpy() - env.co.apply_segments(E[None], 2, w)) < 1e-13
 
 
-@pytest.fixture(params=["ws", "simple"])
+@pytest.fixture(params=["fast", "ws", "simple"])
 def bps_kernel(request, monkeypatch):
-    """Both BPS kernels: warp-specialised (default) and phase-by-phase."""
-    if request.param == "simple":
-        monkeypatch.setenv("QB_BPS_KERNEL", "simple")
-    else:
+    """All BPS kernels: column-per-lane (default where it applies: c64, rectangular alphabet, A a multiple
+    of 32), warp-specialised tiles, phase-by-phase tiles."""
+    if request.param == "fast":
         monkeypatch.delenv("QB_BPS_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("QB_BPS_KERNEL", request.param)
     return request.param
 
 
 @pytest.mark.parametrize("M,A,N", [(32, 32, 11), (64, 64, 45), (4, 16, 5), (128, 48, 20), (256, 64, 32),
-                                   (16, 100, 70)])
+                                   (16, 100, 70), (16, 32, 21), (64, 96, 8), (16, 128, 33), (4, 32, 1),
+                                   (64, 64, 16), (64, 64, 100)])
 def test_bps_slicer_and_bruteforce_vs_oracle(env, bps_kernel, M, A, N):
     """Cross constellations (32/128) have no rectangular grid -> brute force; square ones use the
     slicer, which must give the same bits as brute force and as the oracle."""
