@@ -42,54 +42,17 @@ struct BpsFastParams {
     int A, n_re, n_im, N;
 };
 
-// (s*v.x, s*v.y), each product rounded once (FMUL2 with a broadcast scalar operand)
-__device__ __forceinline__ float2 mul2_bcast(float s, float2 v)
-{
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc;\n\t"
-        "mov.b64 ra, {%2, %2};\n\t"
-        "mov.b64 rb, {%3, %4};\n\t"
-        "mul.rn.f32x2 rc, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rc;}"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(s), "f"(v.x), "f"(v.y));
-    return r;
-}
-// (s+v.x, s+v.y)  (FADD2).  Never feed it a packed product: ptxas would contract the pair into FFMA2.
-__device__ __forceinline__ float2 add2_bcast(float s, float2 v)
-{
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc;\n\t"
-        "mov.b64 ra, {%2, %2};\n\t"
-        "mov.b64 rb, {%3, %4};\n\t"
-        "add.rn.f32x2 rc, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rc;}"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(s), "f"(v.x), "f"(v.y));
-    return r;
-}
-// (a.x*a.x, a.y*a.y)
-__device__ __forceinline__ float2 sqr2(float2 a)
-{
-    float2 r;
-    asm("{.reg .b64 ra, rc;\n\t"
-        "mov.b64 ra, {%2, %3};\n\t"
-        "mul.rn.f32x2 rc, ra, ra;\n\t"
-        "mov.b64 {%0, %1}, rc;}"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(a.x), "f"(a.y));
-    return r;
-}
 __device__ __forceinline__ float fma_sat(float a, float b, float c)
 {
     float r;
     asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-__device__ __forceinline__ float2 lds_f2(uint32_t addr)
+// slicer table entry: read-only after initialisation, so the load is a pure function of the address
+__device__ __forceinline__ f32x2 lds_tab(uint32_t addr)
 {
-    float2 r;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    f32x2 r;
+    asm("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr));
     return r;
 }
 
@@ -120,7 +83,7 @@ __device__ __forceinline__ float axis_min_fast(float t, const FastAxis &g)
 {
     const float u = fma_sat(t, g.s1, g.b1);
     const float w = fmaf(u, g.nm1, 12582912.f);
-    const float2 nl = lds_f2((__float_as_uint(w) << 3) + g.kaddr);
+    const f32x2 nl = lds_tab((__float_as_uint(w) << 3) + g.kaddr);
     const float2 df = add2_bcast(t, nl);
     return fminf(fabsf(df.x), fabsf(df.y));
 }
@@ -209,8 +172,16 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
 
     // ---- this lane's angle column ------------------------------------------------------------------
     const float2 cc = p.comp[warp * 32 + lane];
-    const float2 c1 = make_float2(cc.x, cc.y);      // e.x * (cr,  ci)
-    const float2 c2 = make_float2(-cc.y, cc.x);     // e.y * (-ci, cr)   (negation commutes with rounding)
+    // e.x * (cr, ci) and e.y * (-ci, cr) (negation commutes with rounding).  Both constants are read back
+    // from shared memory as 64-bit values: a pair that ptxas can re-derive from cc is re-packed with
+    // MOV + FADD in every group of the inner loop.
+    f32x2 c1, c2;
+    {
+        float4 *bounce = reinterpret_cast<float4 *>(part) + tid;   // part[] is not in use yet
+        *bounce = make_float4(cc.x, cc.y, -cc.y, cc.x);
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c1), "=l"(c2) : "r"(smem_u32(bounce)) : "memory");
+        __syncthreads();
+    }
     float csum = 0.f;
     const uint32_t ring_lo = smem_u32(ring_w) + 4u * lane;
     const uint32_t stage_addr = smem_u32(stage + warp * FAST_TR);
@@ -228,10 +199,10 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     auto group = [&](bool first, int rbase, uint32_t aA, uint32_t aB) {
         float2 e[4];
         float old[4], c[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[u].x), "=f"(e[u].y)
-                         : "r"(stage_addr + 8u * (rbase + u)));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(e[0].x), "=f"(e[0].y), "=f"(e[1].x), "=f"(e[1].y)
+                     : "r"(stage_addr + 8u * rbase));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(e[2].x), "=f"(e[2].y), "=f"(e[3].x), "=f"(e[3].y)
+                     : "r"(stage_addr + 8u * rbase));
         // csum[i - 2N] (0 while i < 2N: unused)
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[0]) : "r"(aA));
         asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[1]) : "r"(aA));
@@ -280,15 +251,21 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
         // rows past the end of the stream (last group only) run on stale inputs: they come after every
         // valid row in the running sums and are masked in the tail
         const int ngroups = (nrows + 3) >> 2;
+        int g = 0;
+        if (m == 0) {                                  // the stream's first group: row 0 contributes nothing
+            group(true, 0, ring_lo, ring_lo + 256u);
+            slot = 4 == W ? 0 : 4;
+            g = 1;
+        }
 #pragma unroll 1
-        for (int g = 0; g < ngroups; g++) {
+        for (; g < ngroups; g++) {
             const uint32_t aA = ring_lo + 128u * (uint32_t)slot;
             if (slot + 4 <= W) {
-                group(m == 0 && g == 0, 4 * g, aA, aA + 256u);
+                group(false, 4 * g, aA, aA + 256u);
                 slot += 4;
                 if (slot == W) slot = 0;
             } else {                                   // slot == W - 2: rows 2,3 wrap to slots 0,1
-                group(m == 0 && g == 0, 4 * g, aA, ring_lo);
+                group(false, 4 * g, aA, ring_lo);
                 slot = 2;
             }
         }

@@ -68,6 +68,72 @@ __device__ __forceinline__ T shfl_idx(T v, int l)
     return __shfl_sync(0xffffffffu, v, l);
 }
 
+// ---- packed fp32 (Blackwell FMUL2 / FADD2 / FFMA2) -------------------------------------------------
+// Pairs are carried as 64-bit values so that ptxas keeps them in aligned register pairs.  One packed
+// instruction does two IEEE operations in one issue slot (the FP32 pipe still spends two cycles on it).
+// NOTE: ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 although both carry .rn --
+// where the unfused result matters (BPS), the addition after a packed product must be a scalar add.rn.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+// (s*v.x, s*v.y), each product rounded once (FMUL2 with a broadcast scalar operand)
+__device__ __forceinline__ float2 mul2_bcast(float s, f32x2 v)
+{
+    f32x2 r;
+    asm("{.reg .b64 ra;\n\t"
+        "mov.b64 ra, {%1, %1};\n\t"
+        "mul.rn.f32x2 %0, ra, %2;}"
+        : "=l"(r)
+        : "f"(s), "l"(v));
+    return unpack2(r);
+}
+// (s+v.x, s+v.y)  (FADD2).  Never feed it a packed product where the unfused sum is required.
+__device__ __forceinline__ float2 add2_bcast(float s, f32x2 v)
+{
+    f32x2 r;
+    asm("{.reg .b64 ra;\n\t"
+        "mov.b64 ra, {%1, %1};\n\t"
+        "add.rn.f32x2 %0, ra, %2;}"
+        : "=l"(r)
+        : "f"(s), "l"(v));
+    return unpack2(r);
+}
+// (a.x*a.x, a.y*a.y)
+__device__ __forceinline__ float2 sqr2(float2 a)
+{
+    f32x2 r;
+    const f32x2 v = pack2(a.x, a.y);
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(v));
+    return unpack2(r);
+}
+// acc + s*v: two fused multiply-adds in one FFMA2 (scalar s broadcast)
+__device__ __forceinline__ f32x2 fma2_bcast(float s, f32x2 v, f32x2 acc)
+{
+    f32x2 r;
+    asm("{.reg .b64 ra;\n\t"
+        "mov.b64 ra, {%1, %1};\n\t"
+        "fma.rn.f32x2 %0, ra, %2, %3;}"
+        : "=l"(r)
+        : "f"(s), "l"(v), "l"(acc));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---- async copy (LDGSTS) and TMA bulk copy (UBLKCP) + mbarrier -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
