@@ -1,7 +1,5 @@
-// Instantiations of the LPS = 8 lanes-per-stream training kernels (eq_train_fast.cuh, eq_train_la.cuh).
-#include <stdlib.h>
-
-#include "eq_train_la.cuh"
+// Instantiations of the LPS = 8 lanes-per-stream training kernel (eq_train_fast.cuh).
+#include "eq_train_fast.cuh"
 
 namespace qb {
 
@@ -12,19 +10,6 @@ int train_fast_l8(TrainParams<float> p, cudaStream_t st)
     size_t smem = 0;
     const int nq = fast_geometry<8>(p, g, smem, 16);
     if (!nq) return 0;
-    // QB_TRAIN_LA=1 selects the look-ahead form of the recurrence (eq_train_la.cuh).  It is exact algebra
-    // and parity-tested, but measured SLOWER than the direct form on B200 (394 vs 310 cycles per symbol,
-    // profiles/README.md): ptxas does not overlap the extra work with the shuffle latency.  Kept opt-in.
-    const char *la = getenv("QB_TRAIN_LA");
-    if (la && la[0] == '1') {
-        int r = 0;
-        switch (nq) {
-        case 6: r = try_la<8, 6>(p, g, st); break;
-        case 12: r = try_la<8, 12>(p, g, st); break;
-        default: break;
-        }
-        if (r != 0) return r;
-    }
     int rc;
     switch (nq) {
     case 2: rc = launch_sub_method<8, 2>(p, g, smem, st); break;

@@ -80,6 +80,13 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
+// same, but opaque to ptxas (it otherwise re-derives / duplicates a cheap pair at every use)
+__device__ __forceinline__ f32x2 pack2_opaque(float lo, float hi)
+{
+    f32x2 r;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 __device__ __forceinline__ float2 unpack2(f32x2 v)
 {
     float2 r;
@@ -125,6 +132,25 @@ __device__ __forceinline__ f32x2 fma2_bcast(float s, f32x2 v, f32x2 acc)
         "fma.rn.f32x2 %0, ra, %2, %3;}"
         : "=l"(r)
         : "f"(s), "l"(v), "l"(acc));
+    return r;
+}
+// element-wise a*b + c (FFMA2)
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
