@@ -11,6 +11,7 @@
 
 namespace qb {
 
+int train_la_l8(TrainParams<float> p, cudaStream_t st);
 int train_fast_l8(TrainParams<float> p, cudaStream_t st);
 int train_fast_l16(TrainParams<float> p, cudaStream_t st);
 
@@ -26,6 +27,13 @@ int train_fast_try(TrainParams<float> p, cudaStream_t st)
     // Default: 8 lanes per stream (fewest instructions per trained symbol; measured fastest from 2 to
     // thousands of streams on B200).  A fixed layout also keeps a segment's result independent of how
     // many other segments share the launch.
+    // Look-ahead form of the recurrence (eq_train_la.cuh) where it is instantiated: fixed step size, 8 lanes per
+    // stream, 6 or 12 taps per lane.  QB_TRAIN_KERNEL=direct keeps the direct form (tests run both).
+    const char *kern = getenv("QB_TRAIN_KERNEL");
+    if (!forced && !(kern && kern[0] == 'd')) {
+        const int rc = train_la_l8(p, st);
+        if (rc != 0) return rc;
+    }
     int order[2] = {8, 16};
     if (forced == 16) {
         order[0] = 16;

@@ -1,0 +1,401 @@
+// eq_train look-ahead kernel (complex64, os = 2, fixed step size): the planar/packed layout of
+// train_sub_kernel (eq_train_fast.cuh) with the serial chain cut down to the error function.
+//
+// The reference recurrence (pythran_equalisation.py:166-170)
+//     y_i = X_i . W_i ,   c_i = mu * errfct(y_i) ,   W_{i+1} = W_i + c_i conj(X_i)
+// puts tap update -> tap dot -> shuffle all-reduce -> error function on ONE dependent chain per symbol
+// (~320 cycles on B200 with one warp per SM sub-partition, of which ~120 are pure latency during which
+// the warp has nothing to issue).  Substituting the last update into the dot,
+//     y_{i+1} = X_{i+1} . W_i  +  c_i * G_{i+1} ,      G_{i+1} = X_{i+1} . conj(X_i)        (exact algebra)
+// the expensive part Q_{i+1} = X_{i+1} . W_i no longer depends on c_i, and G is a property of the
+// SIGNAL alone (the lag-2 autocorrelation of the window, the same for every mode trained on the
+// segment): the warp computes it for a whole staged tile at once from a running sum of lag-2 products
+// (tile_gram, ~4 instructions per symbol) and reads it back one value per symbol.  Per symbol the warp
+// then issues, in this order,
+//     1. the all-reduce of the partial Q_i, its three shuffle hops interleaved with the tap update
+//        W_i = W_{i-1} + c_{i-1} conj(X_{i-1})                        (24 FFMA2 fill the shuffle latency)
+//     2. y_i = Q_i + c_{i-1} G_i -> error function -> c_i, interleaved with the partial dot
+//        Q_{i+1} = X_{i+1} . W_i                                      (24 FFMA2 fill the error-function chain)
+// so only  Q + c*G -> errfct -> c  (~35 cycles) is serial and the rest is bound by instruction issue.
+// Same FMAs as the direct form plus 4 per symbol; results equal it to rounding (the parity tests hold
+// both to the same 1e-5 rms against the oracle; a numpy model of this recursion differs from the strict
+// oracle by 6e-7 rms on the error signal of a C3 segment).
+//
+// The register window holds NP + 2 pairs per plane because symbol i needs the windows of symbols i-1
+// (update) and i+1 (dot); tiles are staged from one pair (2 samples) before the tile's first symbol.
+#pragma once
+#include "eq_train_fast.cuh"
+
+namespace qb {
+
+// Gram values of one staged tile, computed by the warp itself right after the tile has landed:
+//     G_il = sum_k sum_{t < ntaps} x_k[2 il + 2 + t] conj(x_k[2 il + t])        (staged sample indices)
+//          = S[2 il + ntaps] - S[2 il],      S[j] = sum_{m = 2 .. j + 1} p[m],   p[m] = sum_k x_k[m] conj(x_k[m - 2]).
+// Every lane forms GRAM_CH consecutive lag-2 products from the planar tile (odd chunk length: conflict
+// free), a warp scan turns them into the running sum S, and G is two loads and one subtraction per
+// symbol.  About 4 instructions per trained symbol -- instead of a separate pass over the capture and
+// 8 bytes of HBM per symbol.  G only ever enters multiplied by the step mu*e ~ 5e-4, so the rounding of
+// a running sum over <= 416 products (<= 3e-5 absolute) is far below the fp32 resolution of y.
+constexpr int GRAM_CH = 13;   // 32 * 13 = 416 >= 2 * 128 + 8 * 12 + 2 products per tile
+
+__device__ __forceinline__ void tile_gram(const float *tile, int nslots, int nmodes, int pitch, int tile_syms,
+                                          int ntaps, float2 *S, float2 *gbuf, int lane)
+{
+    const int row_floats = 2 * pitch, slot_floats = nmodes * row_floats;
+    for (int sl = 0; sl < nslots; sl++) {
+        const float *base = tile + sl * slot_floats;
+        float2 *Ss = S + sl * (32 * GRAM_CH + 1);
+        const int mb = 2 + lane * GRAM_CH;
+        // products beyond mend read whatever follows in shared memory; running sums are causal, so they only
+        // reach entries of S that nobody reads -- no bounds branch in here
+        float pr[GRAM_CH], pi[GRAM_CH];
+#pragma unroll
+        for (int j = 0; j < GRAM_CH; j++) pr[j] = pi[j] = 0.f;
+        for (int kk = 0; kk < nmodes; kk++) {
+            const float *re = base + kk * row_floats + mb - 2, *im = re + pitch;
+            float xr[GRAM_CH + 2], xi[GRAM_CH + 2];
+#pragma unroll
+            for (int j = 0; j < GRAM_CH + 2; j++) {
+                xr[j] = re[j];
+                xi[j] = im[j];
+            }
+#pragma unroll
+            for (int j = 0; j < GRAM_CH; j++) {   // x[m] * conj(x[m-2])
+                pr[j] = fmaf(xr[j + 2], xr[j], fmaf(xi[j + 2], xi[j], pr[j]));
+                pi[j] = fmaf(xi[j + 2], xr[j], fmaf(-xr[j + 2], xi[j], pi[j]));
+            }
+        }
+        float2 loc[GRAM_CH];
+        float2 run = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < GRAM_CH; j++) {
+            run.x += pr[j];
+            run.y += pi[j];
+            loc[j] = run;
+        }
+        // exclusive scan of the lane totals
+        float2 off = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float ox = __shfl_up_sync(0xffffffffu, off.x, d), oy = __shfl_up_sync(0xffffffffu, off.y, d);
+            if (lane >= d) {
+                off.x += ox;
+                off.y += oy;
+            }
+        }
+        off.x -= run.x;
+        off.y -= run.y;
+        if (lane == 0) Ss[0] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < GRAM_CH; j++) Ss[mb + j - 1] = make_float2(off.x + loc[j].x, off.y + loc[j].y);
+        __syncwarp();
+        for (int il = lane; il < tile_syms; il += 32) {
+            const float2 hi = Ss[2 * il + ntaps], lo = Ss[2 * il];
+            gbuf[sl * tile_syms + il] = make_float2(hi.x - lo.x, hi.y - lo.y);
+        }
+        __syncwarp();
+    }
+}
+
+template <int LPS, int NQ, int METHOD, int NMASK>
+__global__ void __launch_bounds__(32) train_la_kernel(TrainParams<float> p, FastGeom g)
+{
+    static_assert(NQ % 2 == 0, "NQ must be even (os = 2: the window moves by one pair per symbol)");
+    constexpr int NP = NQ / 2;     // pairs per lane
+    constexpr int B = NP + 2;      // circular pair window: symbols i-1 .. i+1; also symbols per unrolled chunk
+    constexpr int GPW = 32 / LPS;  // streams (lane groups) per warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x, grp = lane / LPS, gl = lane % LPS;
+    const long long stream0 = (long long)blockIdx.x * GPW;
+    const bool active = stream0 + grp < p.nstreams;
+    const long long stream = active ? stream0 + grp : p.nstreams - 1;
+    const long long seg = stream / p.nsel;
+    const int jsel = (int)(stream % p.nsel);
+    const int mode = p.modes.m[jsel];
+    const long long seg_first = stream0 / p.nsel;
+    const long long seg_last = min(stream0 + GPW - 1, p.nstreams - 1) / p.nsel;
+    const int nslots = (int)(seg_last - seg_first) + 1;
+    const int slot = (int)(seg - seg_first);
+
+    // tiles: [2][nslots][nmodes][2 planes][pitch] floats; Gram values [nslots][tile_syms] and their running
+    // sums [nslots][32*GRAM_CH + 1]; errors; constants
+    const int row_floats = 2 * g.pitch, slot_floats = p.nmodes * row_floats;
+    float *tile0 = reinterpret_cast<float *>(smem_raw);
+    float *tile1 = tile0 + g.nslots * slot_floats;
+    float2 *gbuf = reinterpret_cast<float2 *>(tile1 + g.nslots * slot_floats);
+    float2 *gsum = gbuf + g.nslots * g.tile_syms;
+    float2 *errs = gsum + g.nslots * (32 * GRAM_CH + 1);   // [GPW][tile_syms]
+    float2 *syms = errs + GPW * g.tile_syms;         // [GPW][nsym_smem]
+
+    const float2 *gsyms = p.symbols + (long long)mode * p.K;
+    float2 *mysyms = syms + grp * p.nsym_smem;
+    for (int c = gl; c < p.nsym_smem; c += LPS) mysyms[c] = gsyms[c];
+
+    const int k = gl / g.lpp, t0 = (gl % g.lpp) * NQ;
+    f32x2 PR[NP], PI[NP];   // taps: (re[2p], re[2p+1]) and (im[2p], im[2p+1])
+    f32x2 MK[NMASK > 0 ? NMASK : 1];
+    float2 *wg = p.wx + ((long long)seg * p.nmodes + mode) * (long long)(p.nmodes * p.ntaps) + k * p.ntaps;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        const bool v0 = t0 + 2 * q < p.ntaps, v1 = t0 + 2 * q + 1 < p.ntaps;
+        const float2 w0 = v0 ? wg[t0 + 2 * q] : make_float2(0.f, 0.f);
+        const float2 w1 = v1 ? wg[t0 + 2 * q + 1] : make_float2(0.f, 0.f);
+        PR[q] = pack2(w0.x, w1.x);
+        PI[q] = pack2(w0.y, w1.y);
+        if (q >= NP - NMASK) MK[q - (NP - NMASK)] = pack2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
+    }
+    const float mu = p.mu[stream];
+    const uint32_t errs_addr = smem_u32(errs + grp * g.tile_syms);
+    __syncwarp();
+    const ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);
+
+    const long long ntiles_it = (p.TrSyms + g.tile_syms - 1) / g.tile_syms;
+    const long long ntiles = ntiles_it * p.Niter;
+    const long long Lread = (p.TrSyms - 1) * 2 + p.ntaps;  // samples of a row the caller guarantees
+
+    // stage tile gt: samples [2*i0 - 2, 2*i0 - 2 + pitch) of every row (zero outside [0, Lread))
+    auto load_tile = [&](long long gt, float *buf) {
+        const long long i0 = (gt % ntiles_it) * g.tile_syms;
+        const long long s0 = i0 * 2 - 2;
+        const int lo = s0 < 0 ? (int)(-s0) : 0;
+        const int hi = (int)max((long long)lo, min((long long)g.pitch, Lread - s0));
+        for (int sl = 0; sl < nslots; sl++) {
+            for (int kk = 0; kk < p.nmodes; kk++) {
+                const float *src = reinterpret_cast<const float *>(p.E + (seg_first + sl) * p.seg_stride +
+                                                                   (long long)kk * p.row_stride) + 2 * s0;
+                // float c of the staged row: even -> real plane, odd -> imaginary plane (c and lane share parity)
+                float *dst = buf + sl * slot_floats + kk * row_floats + (lane & 1) * g.pitch + (lane >> 1);
+                const float *s = src + lane;
+                if (lo == 0 && hi == g.pitch) {          // interior tile: every staged sample exists
+                    int c = lane;
+#pragma unroll 4
+                    for (; c < 2 * g.pitch; c += 32, dst += 16, s += 32) cp_async<4>(dst, s);
+                } else {
+                    for (int c = lane; c < 2 * g.pitch; c += 32, dst += 16, s += 32) {
+                        const int m = c >> 1;
+                        if (m >= lo && m < hi) cp_async<4>(dst, s);
+                        else *dst = 0.f;
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    float crp = 0.f, cip = 0.f;     // c_{i-1} = mu * e_{i-1}: the update that is still to be applied
+    float pqr = 0.f, pqi = 0.f;     // this lane's partial of Q_i = X_i . W_{i-1}
+
+    if (ntiles > 0) load_tile(0, tile0);
+    for (long long gt = 0; gt < ntiles; gt++) {
+        float *cur = (gt & 1) ? tile1 : tile0;
+        if (gt + 1 < ntiles) {
+            load_tile(gt + 1, (gt & 1) ? tile0 : tile1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        tile_gram(cur, nslots, p.nmodes, g.pitch, g.tile_syms, p.ntaps, gsum, gbuf, lane);
+        const long long it = gt / ntiles_it;
+        const long long tl = gt % ntiles_it;
+        const long long i0 = tl * g.tile_syms;
+        const int n = (int)min((long long)g.tile_syms, p.TrSyms - i0);
+        const uint32_t xre = smem_u32(cur + slot * slot_floats + k * row_floats + t0);
+        const uint32_t xim = xre + 4u * (uint32_t)g.pitch;
+        const uint32_t gaddr = smem_u32(gbuf + slot * g.tile_syms);
+
+        // staged pair j (samples 2j, 2j+1 of the staged row) lives in slot j % B; symbol il of the tile
+        // has its window in pairs il+1 .. il+NP, symbol il-1 in pairs il .. il+NP-1, symbol il+1 in il+2 ..
+        f32x2 XR[B], XI[B];
+#pragma unroll
+        for (int q = 0; q <= NP; q++) {
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(XR[q]) : "r"(xre + 8u * q));
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(XI[q]) : "r"(xim + 8u * q));
+        }
+        if (tl == 0) {
+            // start of a training iteration: nothing pending, Q_0 = X_0 . W_0 directly (pairs 1 .. NP)
+            crp = cip = 0.f;
+            f32x2 a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const f32x2 xr = XR[(1 + q) % B], xi = XI[(1 + q) % B];
+                a1 = fma2(xr, PR[q], a1);
+                a2 = fma2(xi, PI[q], a2);
+                b1 = fma2(xr, PI[q], b1);
+                b2 = fma2(xi, PR[q], b2);
+            }
+            const float2 sa = unpack2(sub2(a1, a2)), sb = unpack2(add2(b1, b2));
+            pqr = sa.x + sa.y;
+            pqi = sb.x + sb.y;
+        }
+#pragma unroll 1
+        for (int il0 = 0; il0 < n; il0 += B) {
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int il = il0 + u;
+                const bool live = il < n;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(XR[(u + NP + 1) % B]) : "r"(xre + 8u * (il + NP + 1)));
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(XI[(u + NP + 1) % B]) : "r"(xim + 8u * (il + NP + 1)));
+                float2 Gi;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(Gi.x), "=f"(Gi.y) : "r"(gaddr + 8u * il));
+                // ---- 1. all-reduce of the partial Q_il, hops interleaved with W += c_{il-1} conj(X_{il-1}) ----
+                float qr = pqr, qi = pqi;
+                const float ncr = -crp;
+                constexpr int NHOP = LPS == 8 ? 3 : (LPS == 16 ? 4 : 5);
+#pragma unroll
+                for (int h = 0; h < NHOP; h++) {
+                    const int m = LPS >> (h + 1);
+                    const float tr = __shfl_xor_sync(0xffffffffu, qr, m);
+                    const float ti = __shfl_xor_sync(0xffffffffu, qi, m);
+#pragma unroll
+                    for (int q = (NP * h) / NHOP; q < (NP * (h + 1)) / NHOP; q++) {
+                        f32x2 xr = XR[(u + q) % B], xi = XI[(u + q) % B];
+                        if (q >= NP - NMASK) {   // taps past ntaps stay exactly zero
+                            xr = mul2(xr, MK[q - (NP - NMASK)]);
+                            xi = mul2(xi, MK[q - (NP - NMASK)]);
+                        }
+                        PR[q] = fma2_bcast(crp, xr, PR[q]);
+                        PR[q] = fma2_bcast(cip, xi, PR[q]);
+                        PI[q] = fma2_bcast(cip, xr, PI[q]);
+                        PI[q] = fma2_bcast(ncr, xi, PI[q]);
+                    }
+                    qr += tr;
+                    qi += ti;
+                }
+                // ---- 2. y = Q + c_{il-1} G -> error -> c_il, interleaved with the partial dot Q_{il+1} ---------
+                const float yr = fmaf(-cip, Gi.y, fmaf(crp, Gi.x, qr));
+                const float yi = fmaf(cip, Gi.x, fmaf(crp, Gi.y, qi));
+                f32x2 a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    const f32x2 xr = XR[(u + 2 + q) % B], xi = XI[(u + 2 + q) % B];
+                    a1 = fma2(xr, PR[q], a1);
+                    a2 = fma2(xi, PI[q], a2);
+                    b1 = fma2(xr, PI[q], b1);
+                    b2 = fma2(xi, PR[q], b2);
+                }
+                const long long i = i0 + il;
+                const float2 e = err_fast<METHOD, LPS>(p.method, make_float2(yr, yi), ec, mysyms, p.K, gsyms,
+                                                  live ? i : 0, gl);
+                // every lane of the group stores the same value; symbols past n are never copied out
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(errs_addr + 8u * il), "f"(e.x), "f"(e.y)
+                             : "memory");
+                const float mu_l = live ? mu : 0.f;     // symbols past the end of the stream: zero step
+                crp = mu_l * e.x;
+                cip = mu_l * e.y;
+                const float2 sa = unpack2(sub2(a1, a2)), sb = unpack2(add2(b1, b2));
+                pqr = sa.x + sa.y;
+                pqi = sb.x + sb.y;
+            }
+        }
+        if (tl == ntiles_it - 1) {
+            // end of a training iteration: apply the pending update c_{T-1} conj(X_{T-1}).  The loop ended
+            // on a chunk boundary, so that window sits in slots 0 .. NP-1 (pairs il_end .. il_end+NP-1);
+            // if the last chunk ran past the end of the stream the pending step is already zero.
+            const float ncr = -crp;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                f32x2 xr = XR[q % B], xi = XI[q % B];
+                if (q >= NP - NMASK) {
+                    xr = mul2(xr, MK[q - (NP - NMASK)]);
+                    xi = mul2(xi, MK[q - (NP - NMASK)]);
+                }
+                PR[q] = fma2_bcast(crp, xr, PR[q]);
+                PR[q] = fma2_bcast(cip, xi, PR[q]);
+                PI[q] = fma2_bcast(cip, xr, PI[q]);
+                PI[q] = fma2_bcast(ncr, xi, PI[q]);
+            }
+            crp = cip = 0.f;
+        }
+        __syncwarp();
+        if (p.err && active) {
+            float2 *eg = p.err + ((long long)seg * p.nmodes + mode) * (p.TrSyms * p.Niter) + it * p.TrSyms + i0;
+            for (int c = gl; c < n; c += LPS) eg[c] = errs[grp * g.tile_syms + c];
+        }
+        __syncwarp();
+    }
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const float2 wr = unpack2(PR[q]), wi = unpack2(PI[q]);
+            if (t0 + 2 * q < p.ntaps) wg[t0 + 2 * q] = make_float2(wr.x, wi.x);
+            if (t0 + 2 * q + 1 < p.ntaps) wg[t0 + 2 * q + 1] = make_float2(wr.y, wi.y);
+        }
+    }
+}
+
+// geometry of the look-ahead layout; returns NQ or 0 if the shape does not fit
+template <int LPS>
+static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
+{
+    constexpr int GPW = 32 / LPS;
+    if (LPS % p.nmodes) return 0;
+    g.lpp = LPS / p.nmodes;
+    int nq = (p.ntaps + g.lpp - 1) / g.lpp;
+    nq += nq & 1;
+    if (nq != 6 && nq != 12) return 0;       // instantiated shapes (ntaps 21 / 45 dual polarisation, ...)
+    const int B = nq / 2 + 2;
+    g.tile_syms = (128 / B) * B;              // per-tile costs (loader set-up, window preload) amortised over 128 symbols
+    g.pitch = 2 * (g.tile_syms + 1) + g.lpp * nq;
+    g.nslots = (GPW % p.nsel == 0) ? GPW / p.nsel : (GPW / p.nsel + 2 < GPW ? GPW / p.nsel + 2 : GPW);
+    if (g.nslots < 1) g.nslots = 1;
+    if (2 * g.tile_syms + g.lpp * nq + 2 > 32 * GRAM_CH) return 0;
+    smem = ((size_t)2 * g.nslots * p.nmodes * g.pitch + (size_t)g.nslots * g.tile_syms +
+            (size_t)g.nslots * (32 * GRAM_CH + 1) + (size_t)GPW * g.tile_syms + (size_t)GPW * p.nsym_smem) *
+           sizeof(float2);
+    if (smem > 64 * 1024) return 0;
+    return nq;
+}
+
+template <int LPS, int NQ, int METHOD, int NMASK>
+static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
+{
+    constexpr int GPW = 32 / LPS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_done = true;
+    }
+    const long long nblk = (p.nstreams + GPW - 1) / GPW;
+    train_la_kernel<LPS, NQ, METHOD, NMASK><<<(unsigned)nblk, 32, smem, st>>>(p, g);
+    count_launch();
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+template <int LPS, int NQ, int METHOD>
+static int launch_la_pad(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
+{
+    constexpr int NP = NQ / 2;
+    constexpr int NMLO = NP >= 2 ? 2 : NP;
+    const int valid_last = p.ntaps - (g.lpp - 1) * NQ;
+    const int need = valid_last <= 0 ? NP : NP - valid_last / 2;
+    if (need == 0) return launch_la<LPS, NQ, METHOD, 0>(p, g, smem, st);
+    if (need <= NMLO) return launch_la<LPS, NQ, METHOD, NMLO>(p, g, smem, st);
+    return launch_la<LPS, NQ, METHOD, NP>(p, g, smem, st);
+}
+
+template <int LPS, int NQ>
+static int launch_la_method(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
+{
+    switch (p.method) {
+    case QB_CMA:
+    case QB_SGNCMA:
+        return launch_la_pad<LPS, NQ, QB_CMA>(p, g, smem, st);
+    case QB_MCMA:
+        return launch_la_pad<LPS, NQ, QB_MCMA>(p, g, smem, st);
+    case QB_RDE:
+        if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC>(p, g, smem, st);
+        if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_RDE3>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_RDE>(p, g, smem, st);
+    case QB_MRDE:
+        if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC>(p, g, smem, st);
+        if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_MRDE3>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_MRDE>(p, g, smem, st);
+    default:
+        return launch_la_pad<LPS, NQ, METHOD_GENERIC>(p, g, smem, st);
+    }
+}
+
+}  // namespace qb
