@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 METRIC = "Msamples/s dual-pol 64-QAM MCMA->MRDE->BPS"
 # algorithmic bytes per symbol period (dual-pol, os=2, complex64), SURVEY.md section 8d / DESIGN.md
 BYTES_TRAIN, BYTES_APPLY, BYTES_BPS = 48, 48, 40
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at C3 from the ncu --set full captures (profiles/README.md)
+TRAFFIC_TRAIN, TRAFFIC_BPS = 326.1e6, 352.3e6
 
 
 def parse():
@@ -66,53 +68,80 @@ def workload_config(a, world):
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region.  The region lasts tens of milliseconds, so
+    the sampler polls NVML in a thread (about 1 kHz) instead of `nvidia-smi -lms`, whose first line arrives
+    after the region has ended; nvidia-smi is the fallback when pynvml is missing."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.samples.append((float(sm), int(mask)))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.nvml is None:
+            return self._smi_once()
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        n = self.nvml
         try:
-            self.proc.wait(timeout=2)
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            mx = None
+        sm = sorted(v for v, _ in self.samples)
+        mask = 0
+        for _, m in self.samples:
+            mask |= m
+        reasons = [name for name, bit in self.REASONS if mask & bit]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sm), "source": "nvml polled during the timed region"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]),
+                    "reasons": [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi right after the timed region (pynvml unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -264,11 +293,15 @@ def run_b200(a, rank, local_rank, world):
     stage_bytes = {"train": BYTES_TRAIN * nsym_out * len(cfg.methods), "apply": BYTES_APPLY * nsym_out,
                    "bps": BYTES_BPS * nsym_out}
     stage_gbs = {k: stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 for k in stage_ms if stage_ms[k] > 0}
-    kernels = {"train": "train_sub_kernel<8,12,METHOD> (eq_train fast path; two launches per step: mcma, mrde)",
-               "apply": "apply_2x2_os2_kernel", "bps": "bps_kernel<float>"}
-    limits = {"train": "serial-recurrence latency + FP32 issue (60 flop/B at ntaps 45), not HBM",
+    kernels = {"train": "train_la_kernel<8,12,METHOD,2> (look-ahead eq_train; two launches per step: mcma, mrde)",
+               "apply": "apply_2x2_os2_kernel", "bps": "bps_fast_kernel<2>"}
+    limits = {"train": "instruction issue of one warp per SM sub-partition (4 serial streams each; 60 flop/B at "
+                       "ntaps 45), not HBM",
               "apply": "FP32 FMA issue (30 flop/B at ntaps 45), not HBM",
-              "bps": "FP32 issue of the 64-angle distance search + one serial FADD chain per angle, not HBM"}
+              "bps": "instruction issue of the 64-angle distance search (19 instructions per symbol and angle), not HBM"}
+    # algorithmic FP32 FMAs per symbol period: train 2 modes * 2*45 taps * (4 dot + 4 update),
+    # apply 2 * 90 * 4; the BPS search is not FMA work (compares, table look-ups), so it has no entry
+    stage_fma = {"train": 8.0 * 2 * a.ntaps * 2 * nsym_out * len(cfg.methods), "apply": 4.0 * 2 * a.ntaps * 2 * nsym_out}
     dom = max(stage_ms, key=stage_ms.get) if stage_ms else "train"
     peaks = {}
     try:
@@ -280,14 +313,19 @@ def run_b200(a, rank, local_rank, world):
     achieved = stage_gbs.get(dom, 0.0)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
     # workload (profiles/r01_ncu_full_summary.txt); algorithmic bytes per launch are stage_bytes / launches
-    traffic = {"train": 326.1e6, "apply": 450.7e6, "bps": 348.5e6}
+    traffic = {"train": TRAFFIC_TRAIN, "apply": 450.7e6, "bps": TRAFFIC_BPS}
     roofline = {"bound": "hbm", "kernel": kernels[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic.get(dom) if a.nsym == 10 ** 7 else None,
                 "launches_per_step": {"train": len(cfg.methods), "apply": 1, "bps": 1}[dom],
                 "algorithmic_bytes_per_launch": stage_bytes[dom] / {"train": len(cfg.methods), "apply": 1, "bps": 1}[dom],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "binding_limit": limits[dom], "stage_ms_per_step": stage_ms, "stage_gbs": stage_gbs,
-                "stage_frac": {k: v / peak for k, v in stage_gbs.items()}}
+                "stage_frac": {k: v / peak for k, v in stage_gbs.items()},
+                # secondary roof, the one that actually binds these kernels: FP32 FMA issue, 148 SMs x 128 lanes
+                "fp32": {"peak_tfma_per_s": 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12,
+                         "stage_tfma_per_s": {k: stage_fma[k] / (stage_ms[k] * 1e-3) / 1e12
+                                              for k in stage_fma if stage_ms.get(k, 0) > 0},
+                         "note": "fraction of the FP32 pipe = stage_tfma_per_s / peak_tfma_per_s"}}
 
     # end to end: pinned host capture -> H2D -> chain -> D2H of the recovered symbols + phase, with
     # the copies of neighbouring chunks overlapping the compute (pipeline.run_host)

@@ -109,6 +109,10 @@ __device__ __forceinline__ float2 rotate_f(float2 e, float ph)
 }
 
 constexpr int FAST_TR = 32;   // rows per tile (= lanes of the tail)
+#ifndef QB_BPS_NR
+#define QB_BPS_NR 8
+#endif
+constexpr int FAST_NR = QB_BPS_NR;   // rows per group (independent distance evaluations in flight per lane)
 
 template <int NW>
 __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
@@ -191,25 +195,27 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     float2 enext = lane < L ? E[lane] : make_float2(0.f, 0.f);
     uint2 mine = make_uint2(0xffffffffu, 0u);       // (min bits, ballot) of tile row `lane`
 
-    // Four consecutive rows of this lane's column: distance -> running sum -> window difference -> warp
-    // arg-min record.  The four distance evaluations are independent (ILP); only the running sum chains.
-    // Rows 0,1 of the group sit at ring address aA (+128), rows 2,3 at aB (+128): the ring has an even
-    // number of rows and groups start at even slots, so a pair never straddles the wrap.  Shared-memory
-    // accesses are volatile asm in exactly the order wanted: 4 input rows, 4 old sums, 4 new sums.
-    auto group = [&](bool first, int rbase, uint32_t aA, uint32_t aB) {
-        float2 e[4];
-        float old[4], c[4];
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(e[0].x), "=f"(e[0].y), "=f"(e[1].x), "=f"(e[1].y)
-                     : "r"(stage_addr + 8u * rbase));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(e[2].x), "=f"(e[2].y), "=f"(e[3].x), "=f"(e[3].y)
-                     : "r"(stage_addr + 8u * rbase));
-        // csum[i - 2N] (0 while i < 2N: unused)
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[0]) : "r"(aA));
-        asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[1]) : "r"(aA));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[2]) : "r"(aB));
-        asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[3]) : "r"(aB));
+    // FAST_NR consecutive rows of this lane's column: distance -> running sum -> window difference -> warp
+    // arg-min record.  The distance evaluations are independent (ILP); only the running sum chains.
+    // Rows 2k, 2k+1 of the group sit at ring address aP[k] (+128): the ring has an even number of rows and
+    // groups start at even slots, so a pair never straddles the wrap.  Shared-memory accesses are volatile
+    // asm in exactly the order wanted: the input rows, the old sums, the new sums.
+    auto group = [&](bool first, int rbase, const uint32_t (&aP)[FAST_NR / 2]) {
+        float2 e[FAST_NR];
+        float old[FAST_NR], c[FAST_NR];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int k = 0; k < FAST_NR / 2; k++)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(e[2 * k].x), "=f"(e[2 * k].y), "=f"(e[2 * k + 1].x), "=f"(e[2 * k + 1].y)
+                         : "r"(stage_addr + 8u * rbase + 16u * k));
+        // csum[i - 2N] (0 while i < 2N: unused)
+#pragma unroll
+        for (int k = 0; k < FAST_NR / 2; k++) {
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[2 * k]) : "r"(aP[k]));
+            asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[2 * k + 1]) : "r"(aP[k]));
+        }
+#pragma unroll
+        for (int u = 0; u < FAST_NR; u++) {
             const float2 pa = mul2_bcast(e[u].x, c1), pb = mul2_bcast(e[u].y, c2);
             const float tr = __fadd_rn(pa.x, pb.x);     // E[i]*comp[a], unfused (pythran_dsp.py:79)
             const float ti = __fadd_rn(pa.y, pb.y);
@@ -221,20 +227,38 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
         }
         if (first) c[0] = 0.f;                                          // row 0 is never added (:30)
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < FAST_NR; u++) {
             csum = __fadd_rn(csum, c[u]);                               // :33/:36, sequential
             c[u] = csum;
         }
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aA), "f"(c[0]));
-        asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(aA), "f"(c[1]));
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aB), "f"(c[2]));
-        asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(aB), "f"(c[3]));
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int k = 0; k < FAST_NR / 2; k++) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(aP[k]), "f"(c[2 * k]));
+            asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(aP[k]), "f"(c[2 * k + 1]));
+        }
+#pragma unroll
+        for (int u = 0; u < FAST_NR; u++) {
             const unsigned db = __float_as_uint(__fsub_rn(c[u], old[u]));   // >= +0: orders like an unsigned
             const unsigned mn = __reduce_min_sync(FULL, db);
             const unsigned bal = __ballot_sync(FULL, db == mn);
             if (lane == rbase + u) mine = make_uint2(mn, bal);
+        }
+    };
+    auto group_at = [&](bool first, int rbase, int slot) {   // slot: ring slot of the group's first row (even)
+        uint32_t aP[FAST_NR / 2];
+        if (slot + FAST_NR <= W) {                             // no wrap inside the group: immediate offsets
+            const uint32_t aA = ring_lo + 128u * (uint32_t)slot;
+#pragma unroll
+            for (int k = 0; k < FAST_NR / 2; k++) aP[k] = aA + 256u * k;
+            group(first, rbase, aP);
+        } else {
+#pragma unroll
+            for (int k = 0; k < FAST_NR / 2; k++) {
+                int sk = slot + 2 * k;
+                if (sk >= W) sk -= W;
+                aP[k] = ring_lo + 128u * (uint32_t)sk;
+            }
+            group(first, rbase, aP);
         }
     };
 
@@ -250,24 +274,12 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
 
         // rows past the end of the stream (last group only) run on stale inputs: they come after every
         // valid row in the running sums and are masked in the tail
-        const int ngroups = (nrows + 3) >> 2;
-        int g = 0;
-        if (m == 0) {                                  // the stream's first group: row 0 contributes nothing
-            group(true, 0, ring_lo, ring_lo + 256u);
-            slot = 4 == W ? 0 : 4;
-            g = 1;
-        }
+        const int ngroups = (nrows + FAST_NR - 1) / FAST_NR;
 #pragma unroll 1
-        for (; g < ngroups; g++) {
-            const uint32_t aA = ring_lo + 128u * (uint32_t)slot;
-            if (slot + 4 <= W) {
-                group(false, 4 * g, aA, aA + 256u);
-                slot += 4;
-                if (slot == W) slot = 0;
-            } else {                                   // slot == W - 2: rows 2,3 wrap to slots 0,1
-                group(false, 4 * g, aA, ring_lo);
-                slot = 2;
-            }
+        for (int g = 0; g < ngroups; g++) {
+            group_at(m == 0 && g == 0, FAST_NR * g, slot);   // the stream's first row contributes nothing
+            slot += FAST_NR;
+            if (slot >= W) slot -= W;
         }
         __syncwarp();
 
@@ -305,7 +317,9 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
                 float pp = __shfl_up_sync(FULL, p4, 1);
                 if (lane == 0) pp = p4prev;
                 float corr = 0.f;
-                if (valid && j > N) corr = unwrap_corr_f(p4, pp);
+                // np.unwrap only acts where |dd| >= pi: skip its fmod arithmetic for the (usual) tile without such a row
+                const bool cand = valid && j > N && !(fabsf(__fsub_rn(p4, pp)) < 3.14159274101257324219f);
+                if (__any_sync(FULL, cand) && valid && j > N) corr = unwrap_corr_f(p4, pp);
                 unsigned mask = __ballot_sync(FULL, corr != 0.f);
                 float mycum = cum;
                 while (mask) {   // fold the (rare) non-zero corrections in row order: exact sequential sum
@@ -358,7 +372,7 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
                       const void *angles, int64_t A, const void *lev_re, int64_t n_re, const void *lev_im,
                       int64_t n_im, int64_t N, int32_t *idx, void *ph, void *Eout, cudaStream_t st)
 {
-    if (n_re < 1 || n_im < 1 || A % 32 != 0 || A > 128 || N < 2) return 1;   // ring needs >= 4 rows
+    if (n_re < 1 || n_im < 1 || A % 32 != 0 || A > 128 || 2 * N < FAST_NR) return 1;   // a group must fit the ring
     const int NW = (int)(A / 32);
     const size_t smem = fast_smem_bytes(NW, (int)A, (int)n_re, (int)n_im, (int)N);
     if (smem > 100 * 1024) return 1;
