@@ -150,6 +150,9 @@ class ClockSampler:
 def cpu_chain(a, nseg, seed=1234):
     """Times the reference-equivalent CPU chain on `nseg` segments of the workload.  Returns
     (seconds, samples processed, threads)."""
+    # all host threads: torchrun exports OMP_NUM_THREADS=1 to its workers, which would cripple the CPU arm
+    if "cpu_oracle" not in sys.modules:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_oracle as co
@@ -161,6 +164,10 @@ def cpu_chain(a, nseg, seed=1234):
     Es = np.stack([E[:, s * S * 2: s * S * 2 + L_seg] for s in range(nseg)])   # (nseg, 2, L_seg)
     kind = "fast_native"
     lib = co.lib(kind)
+    try:
+        lib.qo_set_threads(int(os.cpu_count() or 1))
+    except Exception:
+        pass
     threads = lib.qo_max_threads()
     alphabet = theory.normalised_symbols(a.M).astype(np.complex64)
     ang = theory.bps_test_angles(a.angles, np.float32)
