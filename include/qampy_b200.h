@@ -63,7 +63,14 @@ typedef enum {
     QB_SBD = 6,      /* :213 sbd_error        */
     QB_SBD_DATA = 7, /* :218 sbd_data_error   */
     QB_MDDMA = 8,    /* :224 mddma_error      */
-    QB_DD = 9        /* :229 ddlms_error      */
+    QB_DD = 9,       /* :229 ddlms_error      */
+    /* error functions of train_equaliser_realvalued (:80-125).  The real-valued trainer runs on the complex
+     * kernels with the imaginary parts held at exactly zero (E, wx and symbols widened by the caller);
+     * these ids select its error functions and the real form of the step-size rule (:18-22). */
+    QB_CMA_REAL = 10,     /* :113 cma_error_real     */
+    QB_SGNCMA_REAL = 11,  /* :117 sgncma_error_real  */
+    QB_DD_REAL = 12,      /* :121 dd_error_real (det_symbol_argmin :232-235) */
+    QB_DD_DATA_REAL = 13  /* :125 dd_data_error_real */
 } qb_method;
 
 #define QB_MAX_MODES 8     /* nmodes (input rows / output modes) per segment            */
@@ -125,7 +132,11 @@ int qb_apply_filter_to_signal_host(int dtype, const void *E, int64_t nmodes, int
  *   idx      (nstream, L) int32 or NULL   -- select_angle_index output (edges 0)
  *   ph       (nstream, L) real  or NULL   -- angles[idx], [N:L-N] unwrapped as np.unwrap(ph*4)/4
  *   Eout     (nstream, L) complex or NULL -- E * exp(+1j*ph)
- * Only a single angle table (testangles.shape[0] == 1) is supported.                          */
+ * qb_bps_* take ONE angle table (testangles.shape[0] == 1, pythran_dsp.py:76-77 ph_idx = 0).
+ * qb_bps_rows_* take a PER-SYMBOL table, comp and angles of shape (nstream, L, A) -- the p == L form
+ * of pythran_dsp.py:74-75 that the second stage of two-stage BPS uses
+ * (qampy/core/phaserecovery.py:276-281).  Only the index search is fused there: ph and Eout must be
+ * NULL (the two-stage tail unwraps the whole array, :282, unlike bps); use qb_select_angles_*.   */
 int qb_bps_dev(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
                const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
                const void *lev_re, int64_t n_re, const void *lev_im, int64_t n_im, int64_t N,
@@ -133,6 +144,13 @@ int qb_bps_dev(int dtype, const void *E, int64_t nstream, int64_t stream_stride,
 int qb_bps_host(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp,
                 const void *angles, int64_t A, const void *symbols, int64_t M, int64_t N,
                 int32_t *idx, void *ph, void *Eout);
+int qb_bps_rows_dev(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
+                    const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
+                    const void *lev_re, int64_t n_re, const void *lev_im, int64_t n_im, int64_t N,
+                    int32_t *idx, void *ph, void *Eout, void *stream);
+int qb_bps_rows_host(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp,
+                     const void *angles, int64_t A, const void *symbols, int64_t M, int64_t N,
+                     int32_t *idx, void *ph, void *Eout);
 
 /* HOST helper: if `symbols` (M complex) is exactly the product set of n_re real levels and n_im
  * imaginary levels (each uniformly spaced), write the sorted levels (capacity 64 each, real type

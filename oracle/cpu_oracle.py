@@ -342,3 +342,102 @@ def bps_driver(E, Mtestangles, symbols, N, kind="strict"):
     if E.ndim == 1:
         return (Ew * np.exp(1.j * ph)).flatten(), ph.flatten()
     return Ew * np.exp(1.j * ph), ph
+
+
+def bps_twostage_driver(E, Mtestangles, symbols, N, B=4, kind="strict"):
+    """phaserecovery.py:222-288: coarse search, per-symbol fine table (p == L form of bps), whole-array
+    unwrap(4*ph, discont=pi)/4, rotate by exp(+1j*ph)."""
+    E = np.asarray(E)
+    rt = E.real.dtype
+    angles = np.linspace(-np.pi / 4, np.pi / 4, Mtestangles, endpoint=False, dtype=rt).reshape(1, -1)
+    Ew = np.atleast_2d(E)
+    ph_out = []
+    for i in range(Ew.shape[0]):
+        idx = bps(np.copy(Ew[i]), angles, symbols, N, kind)
+        ph = select_angles(np.copy(angles), idx, kind)
+        b = np.linspace(-B / 2, B / 2, B)
+        phn = (ph[:, np.newaxis] + b[np.newaxis, :] / (B * Mtestangles) * np.pi / 2).astype(rt)
+        idx2 = bps(np.copy(Ew[i]), phn, symbols, N, kind)
+        phf = select_angles(np.copy(phn), idx2, kind)
+        ph_out.append(np.unwrap(phf * 4, discont=np.pi * 4 / 4) / 4)
+    ph_out = np.asarray(ph_out, dtype=rt)
+    En = Ew * np.exp(1.j * ph_out)
+    if E.ndim == 1:
+        return En.flatten(), ph_out.flatten()
+    return En, ph_out
+
+
+# --------------------------------------------------------------------------------------
+# real-valued trainer (SURVEY.md 8f-4): pure-Python/NumPy restatement, small cases only
+# --------------------------------------------------------------------------------------
+def _adapt_step_real(mu, err_p, err):
+    """pythran_equalisation.py:18-22"""
+    if err * err_p > 0:
+        return mu
+    return mu / (1 + mu * (err * err))
+
+
+def train_equaliser_realvalued(E, TrSyms, Niter, os_, mu, wx, modes, adaptive, symbols, method):
+    """pythran_equalisation.py:80-128, line by line (NumPy scalar semantics of the interpreted reference:
+    ``abs(x)**2``, ``np.sign``, ``np.argmin`` of ``np.abs``).  ``wx`` is updated in place."""
+    def cma(Xest, s1, i):
+        return (s1[0] - abs(Xest) ** 2) * Xest                       # :113-115
+
+    def sgncma(Xest, s1, i):
+        return np.sign(s1[0] - abs(Xest) ** 2) * np.sign(Xest)       # :117-119
+
+    def dd(Xest, symbs, i):
+        dist = np.abs(Xest - symbs)                                  # det_symbol_argmin :232-235
+        symbol = symbs[np.argmin(dist)]
+        return (symbol - Xest) * abs(symbol)                         # :121-123
+
+    def dd_data(Xest, symbs, i):
+        symbol = symbs[i]
+        return (symbol - Xest) * abs(symbol)                         # :125-128
+
+    fct = {"cma": cma, "sgncma": sgncma, "dd": dd, "dd_data": dd_data}
+    if method not in fct:
+        raise ValueError("Unknown method %s" % method)
+    errorfct = fct[method]
+    nmodes = E.shape[0]
+    ntaps = wx.shape[-1]
+    err = np.zeros((nmodes, TrSyms * Niter), dtype=E.dtype)
+    for mode in modes:
+        for it in range(Niter):
+            for i in range(TrSyms):
+                X = E[:, i * os_:i * os_ + ntaps]
+                Xest = E.dtype.type(0)
+                for k in range(nmodes):                              # apply_filter :24-31
+                    for t in range(ntaps):
+                        Xest += X[k, t] * wx[mode, k, t]
+                err[mode, it * TrSyms + i] = errorfct(Xest, symbols[mode], i)
+                wx[mode] += mu * err[mode, it * TrSyms + i] * X
+                if adaptive and i > 0:
+                    mu = _adapt_step_real(mu, err[mode, it * TrSyms + i], err[mode, it * TrSyms + i - 1])
+    return err, wx, mu
+
+
+def equalise_signal_real(E, os_, mu, M, Ntaps, method, TrSyms=None, Niter=1, adaptive=False, symbols=None,
+                         modes=None, apply=True):
+    """equalisation.py:529-565 for the REAL_VALUED methods (cma_real, sgncma_real, dd_real, dd_data_real)."""
+    from qampy_b200 import theory
+    Er = theory.convert_sig_to_real(np.atleast_2d(E))
+    mu = Er.dtype.type(mu)
+    nmodes = Er.shape[0]
+    if modes is None:
+        modes = np.arange(nmodes)
+    else:
+        modes = np.atleast_1d(modes)
+        modes = np.hstack([modes, modes + nmodes // 2])
+    wxy = theory.init_taps(Ntaps, nmodes, Er.dtype)
+    if TrSyms is None:
+        TrSyms = theory.cal_training_symbol_len(os_, Ntaps, Er.shape[-1])
+    symbols = theory.reshape_symbols(symbols, method, M, Er.dtype, nmodes)
+    err, wxy, mu = train_equaliser_realvalued(Er, TrSyms, Niter, os_, mu, wxy, modes, adaptive, symbols.copy(),
+                                              method[:-5])
+    if not apply:
+        return wxy, err
+    ct = np.complex64 if Er.dtype == np.float32 else np.complex128
+    out = apply_filter_to_signal(Er.astype(ct), os_, wxy.astype(ct), modes).real
+    Im = np.complex64(1j) if Er.itemsize == 4 else np.complex128(1j)
+    return theory.convert_sig_to_cmplx(out, modes.shape[0], Im), wxy, err

@@ -38,6 +38,7 @@ struct BpsParams {
     long long stream_stride, L;
     int A, M, n_re, n_im, N;
     int tile_rows, ring_rows;
+    int comp_rows;   // 0: one table comp[A]; 1: per-symbol table comp[L][A] per stream (two-stage BPS, :74-77)
 };
 
 // Per-axis slicer.  `pairs[f] = (lev[f], lev[f+1])` are the two levels bracketing a value whose
@@ -229,7 +230,15 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
         if (tid < nrows) Et[tid] = E[i0 + tid];
         __syncthreads();
         // ---- phase 1: distances of the tile into the ring ---------------------------------------
-        if (fixed) {
+        if (p.comp_rows) {
+            // per-symbol test angles: comp[(i0 + r) * A + a] of this stream (pythran_dsp.py:74-77, ph_idx = i)
+            const cx<T> *crow = p.comp + ((long long)blockIdx.x * L + i0) * A;
+            for (int f = tid; f < nrows * A; f += BPS_THREADS) {
+                const int r = f / A, a = f - r * A;
+                ring[(size_t)(slot0 + r) * A + a] =
+                    min_distance<T>(Et[r], crow[f], slicer, pre, pim, gre, gim, syms, p.M);
+            }
+        } else if (fixed) {
             T *dst = ring + (size_t)slot0 * A + my_a;
             for (int r = my_r0; r < nrows; r += rstep)
                 dst[r * A] = min_distance<T>(Et[r], my_c, slicer, pre, pim, gre, gim, syms, p.M);
@@ -272,7 +281,9 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
             }
             if (idx && valid) idx[j] = bk;
             if (ph) {
-                const T p4 = mul_rn(angs[bk], (T)4);
+                // select_angles: angles[0, idx] or, with a per-symbol table, angles[j, idx] (pythran_dsp.py:137-153)
+                const T ang = (p.comp_rows && valid) ? p.angles[((long long)blockIdx.x * L + j) * A + bk] : angs[bk];
+                const T p4 = mul_rn(ang, (T)4);
                 T pp = __shfl_up_sync(0xffffffffu, p4, 1);
                 if (lane == 0) pp = p4prev;
                 T corr = (T)0;
@@ -509,7 +520,7 @@ template <typename T>
 static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
                       const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
                       const void *lev_re, int64_t n_re, const void *lev_im, int64_t n_im, int64_t N,
-                      int32_t *idx, void *ph, void *Eout, cudaStream_t st)
+                      int32_t *idx, void *ph, void *Eout, int comp_rows, cudaStream_t st)
 {
     if (nstream == 0 || L == 0) return QB_OK;
     BpsParams<T> p;
@@ -529,6 +540,7 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     p.n_re = (int)n_re;
     p.n_im = (int)n_im;
     p.N = (int)N;
+    p.comp_rows = comp_rows;
     const int W = 2 * (int)N;
     // ring: power of two >= TR + 2N rows (so a tile never wraps and slots are a mask away)
     int RR = 2 * BPS_TR;
@@ -550,6 +562,7 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     // default: column-per-lane kernel (bps_fast.cu) where it applies, else the warp-specialised tile kernel;
     // QB_BPS_KERNEL=ws / simple select the tile kernels (tests run all three)
     const char *force = getenv("QB_BPS_KERNEL");
+    if (comp_rows) force = "simple";   // per-symbol angle tables: phase-by-phase kernel only
     if (sizeof(T) == 4 && !(force && (force[0] == 's' || force[0] == 'w'))) {
         const int rc = bps_fast_dispatch(E, nstream, stream_stride, L, comp, angles, A, lev_re, n_re, lev_im, n_im,
                                          N, idx, ph, Eout, st);
@@ -579,13 +592,13 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
 int bps_dispatch(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
                  const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
                  const void *lev_re, int64_t n_re, const void *lev_im, int64_t n_im, int64_t N,
-                 int32_t *idx, void *ph, void *Eout, cudaStream_t st)
+                 int32_t *idx, void *ph, void *Eout, int comp_rows, cudaStream_t st)
 {
     if (dtype == QB_C64)
         return launch_bps<float>(E, nstream, stream_stride, L, comp, angles, A, symbols, M, lev_re, n_re,
-                                 lev_im, n_im, N, idx, ph, Eout, st);
+                                 lev_im, n_im, N, idx, ph, Eout, comp_rows, st);
     return launch_bps<double>(E, nstream, stream_stride, L, comp, angles, A, symbols, M, lev_re, n_re,
-                              lev_im, n_im, N, idx, ph, Eout, st);
+                              lev_im, n_im, N, idx, ph, Eout, comp_rows, st);
 }
 
 // ---- select_angles -----------------------------------------------------------------------------------

@@ -36,7 +36,7 @@ int train_dispatch(int dtype, const void *E, int64_t nseg, int64_t seg_stride, i
 int bps_dispatch(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
                  const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
                  const void *lev_re, int64_t n_re, const void *lev_im, int64_t n_im, int64_t N,
-                 int32_t *idx, void *ph, void *Eout, cudaStream_t st);
+                 int32_t *idx, void *ph, void *Eout, int comp_rows, cudaStream_t st);
 int select_angles_dispatch(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
                            int64_t L, void *out, cudaStream_t st);
 
@@ -196,14 +196,15 @@ static int train_check(int dtype, const void *E, int64_t nseg, int64_t nmodes, i
                        const void *symbols, int64_t K, int method, const void *mu)
 {
     QB_TRY(check_dtype(dtype));
-    QB_REQUIRE(method >= QB_CMA && method <= QB_DD, "Unknown method %d", method);
+    QB_REQUIRE(method >= QB_CMA && method <= QB_DD_DATA_REAL, "Unknown method %d", method);
     QB_REQUIRE(E && wx && symbols && mu, "E, wx, symbols and mu must not be NULL");
     QB_REQUIRE(nseg >= 0 && TrSyms >= 0 && Niter >= 0, "nseg, TrSyms and Niter must be non-negative");
     QB_REQUIRE(os >= 1, "oversampling factor must be larger than 0");
     QB_REQUIRE(ntaps >= 1, "ntaps must be >= 1");
     QB_TRY(check_modes(modes, nsel, nmodes));
     QB_REQUIRE(K >= 1, "symbols must hold at least one value per mode");
-    QB_REQUIRE(method != QB_SBD_DATA || K >= TrSyms, "sbd_data needs at least TrSyms training symbols per mode");
+    QB_REQUIRE((method != QB_SBD_DATA && method != QB_DD_DATA_REAL) || K >= TrSyms,
+               "data-aided methods need at least TrSyms training symbols per mode");
     if (nmodes * ntaps > QB_MAX_TAPDIM)
         return set_error(QB_ERR_UNSUPPORTED, "nmodes*ntaps = %lld exceeds %d", (long long)(nmodes * ntaps),
                          QB_MAX_TAPDIM);
@@ -332,7 +333,19 @@ int qb_bps_dev(int dtype, const void *E, int64_t nstream, int64_t stream_stride,
 {
     QB_TRY(bps_check(dtype, E, nstream, L, comp, angles, A, symbols, M, n_re, n_im, N, ph, Eout));
     return bps_dispatch(dtype, E, nstream, stream_stride, L, comp, angles, A, symbols, M, lev_re, n_re, lev_im,
-                        n_im, N, idx, ph, Eout, (cudaStream_t)stream);
+                        n_im, N, idx, ph, Eout, 0, (cudaStream_t)stream);
+}
+
+int qb_bps_rows_dev(int dtype, const void *E, int64_t nstream, int64_t stream_stride, int64_t L, const void *comp,
+                    const void *angles, int64_t A, const void *symbols, int64_t M, const void *lev_re,
+                    int64_t n_re, const void *lev_im, int64_t n_im, int64_t N, int32_t *idx, void *ph, void *Eout,
+                    void *stream)
+{
+    QB_TRY(bps_check(dtype, E, nstream, L, comp, angles, A, symbols, M, n_re, n_im, N, ph, Eout));
+    if (ph || Eout)   // the reference's two-stage tail differs from bps' (whole-array unwrap, phaserecovery.py:282)
+        return set_error(QB_ERR_UNSUPPORTED, "qb_bps_rows: only the index search is fused; ph and Eout must be NULL");
+    return bps_dispatch(dtype, E, nstream, stream_stride, L, comp, angles, A, symbols, M, lev_re, n_re, lev_im,
+                        n_im, N, idx, ph, Eout, 1, (cudaStream_t)stream);
 }
 
 int qb_detect_grid_host(int dtype, const void *symbols, int64_t M, void *lev_re, int64_t *n_re, void *lev_im,
@@ -346,8 +359,27 @@ int qb_detect_grid_host(int dtype, const void *symbols, int64_t M, void *lev_re,
     return detect_grid<double>((const double *)symbols, M, (double *)lev_re, n_re, (double *)lev_im, n_im);
 }
 
+static int bps_host_impl(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp, const void *angles,
+                         int64_t A, const void *symbols, int64_t M, int64_t N, int32_t *idx, void *ph, void *Eout,
+                         int comp_rows);
+
 int qb_bps_host(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp, const void *angles,
                 int64_t A, const void *symbols, int64_t M, int64_t N, int32_t *idx, void *ph, void *Eout)
+{
+    return bps_host_impl(dtype, E, nstream, L, comp, angles, A, symbols, M, N, idx, ph, Eout, 0);
+}
+
+int qb_bps_rows_host(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp, const void *angles,
+                     int64_t A, const void *symbols, int64_t M, int64_t N, int32_t *idx, void *ph, void *Eout)
+{
+    if (ph || Eout)
+        return set_error(QB_ERR_UNSUPPORTED, "qb_bps_rows: only the index search is fused; ph and Eout must be NULL");
+    return bps_host_impl(dtype, E, nstream, L, comp, angles, A, symbols, M, N, idx, ph, Eout, 1);
+}
+
+static int bps_host_impl(int dtype, const void *E, int64_t nstream, int64_t L, const void *comp, const void *angles,
+                         int64_t A, const void *symbols, int64_t M, int64_t N, int32_t *idx, void *ph, void *Eout,
+                         int comp_rows)
 {
     QB_TRY(bps_check(dtype, E, nstream, L, comp, angles, A, symbols, M, 0, 0, N, ph, Eout));
     cudaStream_t st;
@@ -362,8 +394,9 @@ int qb_bps_host(int dtype, const void *E, int64_t nstream, int64_t L, const void
     const size_t nE = (size_t)nstream * L;
     DevBuf dE(st), dC(st), dA(st), dS(st), dLr(st), dLi(st), dI(st), dP(st), dO(st);
     QB_TRY(dE.alloc(nE * cs));
-    QB_TRY(dC.alloc(A * cs));
-    QB_TRY(dA.alloc(A * rs));
+    const size_t nT = comp_rows ? nE * (size_t)A : (size_t)A;   // one table, or one per symbol and stream
+    QB_TRY(dC.alloc(nT * cs));
+    QB_TRY(dA.alloc(nT * rs));
     QB_TRY(dS.alloc(M * cs));
     QB_TRY(dLr.alloc(64 * rs));
     QB_TRY(dLi.alloc(64 * rs));
@@ -371,15 +404,16 @@ int qb_bps_host(int dtype, const void *E, int64_t nstream, int64_t L, const void
     if (ph) QB_TRY(dP.alloc(nE * rs));
     if (Eout) QB_TRY(dO.alloc(nE * cs));
     QB_CUDA_CHECK(cudaMemcpyAsync(dE.p, E, nE * cs, cudaMemcpyHostToDevice, st));
-    QB_CUDA_CHECK(cudaMemcpyAsync(dC.p, comp, A * cs, cudaMemcpyHostToDevice, st));
-    if (angles) QB_CUDA_CHECK(cudaMemcpyAsync(dA.p, angles, A * rs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dC.p, comp, nT * cs, cudaMemcpyHostToDevice, st));
+    if (angles) QB_CUDA_CHECK(cudaMemcpyAsync(dA.p, angles, nT * rs, cudaMemcpyHostToDevice, st));
     QB_CUDA_CHECK(cudaMemcpyAsync(dS.p, symbols, M * cs, cudaMemcpyHostToDevice, st));
     if (n_re) {
         QB_CUDA_CHECK(cudaMemcpyAsync(dLr.p, lre, n_re * rs, cudaMemcpyHostToDevice, st));
         QB_CUDA_CHECK(cudaMemcpyAsync(dLi.p, lim, n_im * rs, cudaMemcpyHostToDevice, st));
     }
     QB_TRY(bps_dispatch(dtype, dE.p, nstream, L, L, dC.p, angles ? dA.p : nullptr, A, dS.p, M, dLr.p, n_re, dLi.p,
-                        n_im, N, idx ? (int32_t *)dI.p : nullptr, ph ? dP.p : nullptr, Eout ? dO.p : nullptr, st));
+                        n_im, N, idx ? (int32_t *)dI.p : nullptr, ph ? dP.p : nullptr, Eout ? dO.p : nullptr,
+                        comp_rows, st));
     if (idx) QB_CUDA_CHECK(cudaMemcpyAsync(idx, dI.p, nE * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (ph) QB_CUDA_CHECK(cudaMemcpyAsync(ph, dP.p, nE * rs, cudaMemcpyDeviceToHost, st));
     if (Eout) QB_CUDA_CHECK(cudaMemcpyAsync(Eout, dO.p, nE * cs, cudaMemcpyDeviceToHost, st));

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(32) train_warp_kernel(TrainParams<T> p)
                     wi[q] = fma(-cr, x[q].y, wi[q]);
                 }
             }
-            if (p.adaptive && i > 0) mu = adapt_step<T>(mu, e, prev);
+            if (p.adaptive && i > 0)
+                mu = p.method >= QB_CMA_REAL ? adapt_step_real<T>(mu, e.x, prev.x) : adapt_step<T>(mu, e, prev);
             prev = e;
         }
         __syncwarp();
@@ -181,14 +182,15 @@ static int launch_train(const void *E, int64_t nseg, int64_t seg_stride, int64_t
     p.K = (int)K;
     p.modes.n = (int)nsel;
     for (int j = 0; j < nsel; j++) p.modes.m[j] = (int)modes[j];
-    p.nsym_smem = (method == QB_SBD_DATA) ? 0 : (int)K;
+    p.nsym_smem = (method == QB_SBD_DATA || method == QB_DD_DATA_REAL) ? 0 : (int)K;
     p.L = 0;
     p.nstreams = nseg * nsel;
     if (p.nstreams > 2147483647LL) return set_error(QB_ERR_UNSUPPORTED, "train_equaliser: too many streams");
     if (sizeof(T) == 4) {
         // QB_TRAIN_KERNEL=warp forces the generic warp-per-stream kernel (used by the parity tests)
         const char *force = getenv("QB_TRAIN_KERNEL");
-        if (!(force && force[0] == 'w')) {
+        // the real-valued error functions (QB_*_REAL) only exist in the generic kernel
+        if (!(force && force[0] == 'w') && method < QB_CMA_REAL) {
             const int rc = train_fast_try(*reinterpret_cast<TrainParams<float> *>(&p), st);
             if (rc != 0) return rc < 0 ? rc : QB_OK;
         }

@@ -106,6 +106,24 @@ __device__ __forceinline__ cx<T> error_fct(int method, cx<T> x, const cx<T> *sym
         const cx<T> s = det_symbol_warp<T>(x, syms, K, lane);
         return make_cx<T>((s.x * s.x - x.x * x.x) * x.x, (s.y * s.y - x.y * x.y) * x.y);
     }
+    case QB_CMA_REAL: {   // pythran_equalisation.py:113-115, real signal in the real part
+        const T d = syms[0].x - x.x * x.x;
+        return make_cx<T>(d * x.x, (T)0);
+    }
+    case QB_SGNCMA_REAL: {   // :117-119, np.sign(0) = 0
+        const T v = syms[0].x - x.x * x.x;
+        const T d = v > (T)0 ? (T)1 : (v < (T)0 ? (T)-1 : (T)0);
+        const T sx = x.x > (T)0 ? (T)1 : (x.x < (T)0 ? (T)-1 : (T)0);
+        return make_cx<T>(d * sx, (T)0);
+    }
+    case QB_DD_REAL: {   // :121-123 with det_symbol_argmin (:232-235): first minimum of |X - s|
+        const cx<T> s = det_symbol_warp<T>(make_cx<T>(x.x, (T)0), syms, K, lane);
+        return make_cx<T>((s.x - x.x) * fabs(s.x), (T)0);
+    }
+    case QB_DD_DATA_REAL: {   // :125-128
+        const T s = gsyms[i].x;
+        return make_cx<T>((s - x.x) * fabs(s), (T)0);
+    }
     default: {
         const cx<T> s = det_symbol_warp<T>(x, syms, K, lane);
         return make_cx<T>(s.x - x.x, s.y - x.y);
@@ -119,6 +137,13 @@ __device__ __forceinline__ T adapt_step(T mu, cx<T> cur, cx<T> prev)
 {
     if (prev.x * cur.x > 0 && prev.y * cur.y > 0) return mu;
     return mu / ((T)1 + mu * (prev.x * prev.x + prev.y * prev.y));
+}
+// adapt_step_real(mu, err_p = e_i, err = e_{i-1}), pythran_equalisation.py:18-22
+template <typename T>
+__device__ __forceinline__ T adapt_step_real(T mu, T cur, T prev)
+{
+    if (prev * cur > 0) return mu;
+    return mu / ((T)1 + mu * (prev * prev));
 }
 
 }  // namespace qb

@@ -34,10 +34,21 @@ def apply_filter(E, os, wxy, method="pyt", modes=None):
     """Apply the equaliser taps to the signal (decimating by ``os``)."""
     if method not in ("pyt", "py", "cuda"):
         raise NotImplementedError("Only py and pythran methods are implemented")
-    E = _check_complex(E)
     wxy = np.asarray(wxy)
-    if not np.iscomplexobj(wxy):
-        raise NotImplementedError("real-valued taps are not part of the CUDA hot path")
+    if not np.iscomplexobj(wxy) or not np.iscomplexobj(E):
+        # real-valued taps (equalisation.py:177-186): filter the real/imaginary rows, then recombine
+        from . import pythran_equalisation as pe
+        E = np.asarray(E)
+        if np.iscomplexobj(E):
+            E = theory.convert_sig_to_real(np.atleast_2d(_check_complex(E)))
+        modes = np.arange(wxy.shape[0]) if modes is None else np.copy(np.atleast_1d(modes))
+        Etmp = pe.apply_filter_to_signal(np.copy(E), int(os), np.copy(wxy), modes)
+        if E.itemsize == 8:
+            return theory.convert_sig_to_cmplx(Etmp, modes.shape[0], np.complex128(1j))
+        if E.itemsize == 4:
+            return theory.convert_sig_to_cmplx(Etmp, modes.shape[0], np.complex64(1j))
+        raise ValueError("The field has an unknown data type")
+    E = _check_complex(E)
     dev = _dev()
     modes = np.arange(wxy.shape[0]) if modes is None else np.copy(np.atleast_1d(modes))
     assert np.max(modes) < wxy.shape[0], "largest mode number is larger than shape of signal"
@@ -73,7 +84,7 @@ def _train_stage(Ed, os, mu, M, wd, ntaps, TrSyms, Niter, method, adaptive, symb
 def _prepare(E, wxy, Ntaps, modes, method):
     method = method.lower()
     if method in REAL_VALUED:
-        raise NotImplementedError("real-valued equaliser methods (%s) are not part of the CUDA hot path" % method)
+        raise NotImplementedError("real-valued equaliser methods (%s) run through equalise_signal only" % method)
     if method not in _lib.METHODS:
         raise ValueError("Unknown method %s" % method)
     E = np.atleast_2d(_check_complex(E))
@@ -100,6 +111,9 @@ def equalise_signal(E, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, me
     """Blind equalisation with one training method; see the reference docstring for the arguments.
     Returns ``(E_out,) wxy, err``.  A user-supplied ``wxy`` that is already a C-contiguous array of
     the signal's dtype is trained in place, as in the reference (:547)."""
+    if method.lower() in REAL_VALUED:
+        return _equalise_signal_real(E, os, mu, M, wxy, Ntaps, TrSyms, Niter, method.lower(), adaptive_stepsize,
+                                     symbols, modes, apply, **kwargs)
     method, E, nmodes, modes, wxy, wxy_user, Ntaps = _prepare(E, wxy, Ntaps, modes, method)
     dev = _dev()
     Ed = _to_dev(E, dev)[None]
@@ -111,6 +125,37 @@ def equalise_signal(E, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, me
     err = err[0].cpu().numpy()
     if apply:
         return out[0].cpu().numpy(), wxy, err
+    return wxy, err
+
+
+def _equalise_signal_real(E, os, mu, M, wxy, Ntaps, TrSyms, Niter, method, adaptive_stepsize, symbols, modes,
+                          apply, **kwargs):
+    """equalise_signal for the real-valued methods (equalisation.py:529-565): the signal becomes 2*nmodes
+    real rows, taps and error are real, the equalised signal is recombined to complex."""
+    from . import pythran_equalisation as pe
+    E = theory.convert_sig_to_real(np.atleast_2d(_check_complex(E)))
+    mu = E.dtype.type(mu)
+    nmodes = E.shape[0]
+    if modes is None:
+        modes = np.arange(nmodes)
+    else:
+        modes = np.atleast_1d(modes)
+        modes = np.hstack([modes, modes + nmodes // 2])
+        assert np.max(modes) < nmodes, "largest mode number is larger than shape of signal"
+    if wxy is None:
+        wxy = theory.init_taps(Ntaps, nmodes, E.dtype)
+    else:
+        wxy = np.ascontiguousarray(wxy, dtype=E.dtype)
+        Ntaps = wxy.shape[-1]
+        assert wxy.ndim == 3, "wxy needs to be three dimensional"
+        assert wxy.shape[:2] == (nmodes, nmodes), "The first 2 dimensions of wxy need to be the same shape as E"
+    if TrSyms is None:
+        TrSyms = theory.cal_training_symbol_len(os, Ntaps, E.shape[-1])
+    symbols = theory.reshape_symbols(symbols, method, M, E.dtype, nmodes)
+    err, wxy, mu = pe.train_equaliser_realvalued(E, TrSyms, int(Niter), int(os), mu, wxy, modes, adaptive_stepsize,
+                                                 symbols.copy(), method[:-5], kwargs.get("mu_shared", True))
+    if apply:
+        return apply_filter(E, os, wxy, modes=modes), wxy, err
     return wxy, err
 
 

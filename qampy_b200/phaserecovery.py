@@ -29,3 +29,35 @@ def bps(E, Mtestangles, symbols, N, method="pyt", **kwargs):
     if E.ndim == 1:
         return Eout.flatten(), ph.flatten()
     return Eout, ph
+
+
+def bps_twostage(E, Mtestangles, symbols, N, B=4, method="pyt", **kwargs):
+    """Two-stage blind phase search, drop-in for ``qampy/core/phaserecovery.py::bps_twostage`` (:222-288,
+    after Zhuge et al., OFC 2011): a coarse search over ``Mtestangles`` angles, then a search over ``B``
+    angles around every symbol's coarse estimate.  Both index searches run on the GPU (the second one
+    with a per-symbol angle table); angle tables, gathers, ``np.unwrap(4*ph, discont=pi)/4`` over the whole
+    array and the rotation follow the reference line by line in NumPy."""
+    from . import pythran_dsp
+    if method.lower() not in ("pyx", "af", "py", "pyt", "cuda"):
+        raise ValueError("Method needs to be 'pyx', 'py' or 'af'")
+    Ein = E
+    E = np.asarray(E)
+    if E.dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+        raise TypeError("qampy_b200 bps_twostage needs a complex64/complex128 signal, got %s" % E.dtype)
+    rt = E.real.dtype
+    angles = np.linspace(-np.pi / 4, np.pi / 4, Mtestangles, endpoint=False, dtype=rt).reshape(1, -1)   # :270
+    Ew = np.atleast_2d(E)
+    ph_out = []
+    for i in range(Ew.shape[0]):
+        idx = pythran_dsp.bps(np.copy(Ew[i]), angles, symbols, N)
+        ph = pythran_dsp.select_angles(np.copy(angles), idx)
+        b = np.linspace(-B / 2, B / 2, B)
+        phn = (ph[:, np.newaxis] + b[np.newaxis, :] / (B * Mtestangles) * np.pi / 2).astype(rt)   # :277
+        idx2 = pythran_dsp.bps(np.copy(Ew[i]), phn, symbols, N)
+        phf = pythran_dsp.select_angles(np.copy(phn), idx2)
+        ph_out.append(np.unwrap(phf * 4, discont=np.pi * 4 / 4) / 4)                              # :280
+    ph_out = np.asarray(ph_out, dtype=rt)
+    En = np.atleast_2d(Ein).astype(E.dtype) * np.exp(1.j * ph_out)
+    if E.ndim == 1:
+        return En.flatten(), ph_out.flatten()
+    return En, ph_out

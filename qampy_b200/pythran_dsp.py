@@ -23,20 +23,23 @@ def _rtype(dtype):
 
 
 def bps(E, testangles, symbols, N):
-    """Blind phase search index search for one 1-D signal.  ``testangles`` is (1, A); the
-    per-symbol table form (L, A) used by two-stage BPS is not implemented in CUDA."""
+    """Blind phase search index search for one 1-D signal.  ``testangles`` is (1, A) -- one table for
+    every symbol -- or (L, A), one row of test angles per symbol (the second stage of two-stage BPS,
+    ``phaserecovery.py:276-281``; ``pythran_dsp.py:74-77``)."""
     code, rt, ct = _ctype(np.asarray(E).dtype)
     E = np.ascontiguousarray(E, dtype=ct)
     if E.ndim != 1:
         raise ValueError("E must be 1-dimensional")
     testangles = np.atleast_2d(np.asarray(testangles, dtype=rt))
-    if testangles.shape[0] != 1:
-        raise NotImplementedError("per-symbol test-angle tables (two-stage BPS) are not implemented in CUDA")
-    comp = np.ascontiguousarray(np.exp(1j * testangles)[0], dtype=ct)   # pythran_dsp.py:72
+    p, A = testangles.shape
+    if p != 1 and p != E.shape[0]:
+        raise ValueError("p must be either 1 or the length of the input signal")   # pythran_dsp.py:69
+    comp = np.ascontiguousarray(np.exp(1j * testangles), dtype=ct)      # pythran_dsp.py:72 (NumPy's table)
     symbols = np.ascontiguousarray(symbols, dtype=ct).reshape(-1)
     idx = np.zeros(E.shape[0], dtype=np.int32)
-    _lib.check(_lib.load().qb_bps_host(code, _p(E), 1, E.shape[0], _p(comp), None, comp.size, _p(symbols),
-                                       symbols.size, int(N), _p(idx), None, None))
+    fn = _lib.load().qb_bps_host if p == 1 else _lib.load().qb_bps_rows_host
+    _lib.check(fn(code, _p(E), 1, E.shape[0], _p(comp), None, A, _p(symbols), symbols.size, int(N), _p(idx),
+                  None, None))
     return idx
 
 

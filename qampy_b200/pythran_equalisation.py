@@ -22,9 +22,12 @@ def _ctype(dtype):
         return _lib.QB_C64, np.float32, np.complex64
     if dtype == np.complex128:
         return _lib.QB_C128, np.float64, np.complex128
-    if dtype in (np.dtype(np.float32), np.dtype(np.float64)):
-        raise NotImplementedError("real-valued signals/taps are not part of the CUDA hot path")
     raise TypeError("E must be complex64 or complex128, got %s" % dtype)
+
+
+_REAL_TO_CPLX = {np.dtype(np.float32): np.complex64, np.dtype(np.float64): np.complex128}
+# error functions of train_equaliser_realvalued (pythran_equalisation.py:82-91) -> C ABI method ids
+_REAL_METHODS = {"cma": 10, "sgncma": 11, "dd": 12, "dd_data": 13}
 
 
 def _p(a):
@@ -70,11 +73,20 @@ def train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, meth
 
 
 def apply_filter_to_signal(E, os, wx, modes=None):
-    """Static MIMO FIR + decimation: returns (len(modes), (L - ntaps + 1)//os)."""
+    """Static MIMO FIR + decimation: returns (len(modes), (L - ntaps + 1)//os).  Like the reference's
+    export list (:33-36), real E with real wx is accepted: it runs on the complex kernel with the imaginary
+    parts at exactly zero (same products, same order) and the real part is returned."""
     assert os > 0, "oversampling factor must be larger than 0"
-    code, rt, ct = _ctype(np.asarray(E).dtype)
+    Ea = np.asarray(E)
+    if Ea.dtype in _REAL_TO_CPLX:
+        if np.iscomplexobj(wx):
+            raise TypeError("real-valued E needs real-valued wx (pythran_equalisation.py:33-36)")
+        ct = _REAL_TO_CPLX[Ea.dtype]
+        out = apply_filter_to_signal(Ea.astype(ct), os, np.asarray(wx).astype(ct), modes)
+        return np.ascontiguousarray(out.real)
+    code, rt, ct = _ctype(Ea.dtype)
     if not np.iscomplexobj(wx):
-        raise NotImplementedError("real-valued taps are not part of the CUDA hot path")
+        raise TypeError("complex-valued E needs complex-valued wx (pythran_equalisation.py:33-36)")
     E = np.ascontiguousarray(E, dtype=ct)
     wx = np.ascontiguousarray(wx, dtype=ct)
     nmodes_max = wx.shape[0]
@@ -93,6 +105,43 @@ def apply_filter_to_signal(E, os, wx, modes=None):
     return out
 
 
-def train_equaliser_realvalued(*args, **kwargs):
-    raise NotImplementedError("train_equaliser_realvalued (4x4 real MIMO) is outside the CUDA hot path "
-                              "(SURVEY.md section 8f-4)")
+def train_equaliser_realvalued(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, method, mu_shared=True):
+    """Real-valued MIMO trainer (:80-111; the 4x4 real form of a dual-polarisation signal): real ``E``
+    (nmodes, L), real ``wx`` (nmodes, nmodes, ntaps), real ``symbols``; ``method`` in cma / sgncma / dd /
+    dd_data.  Runs on the complex kernels with every imaginary part held at exactly zero -- the real
+    recurrence ``wx += mu * err * X`` is what the complex one does to real data -- with the real-valued
+    error functions and step-size rule selected by their own method ids.  Returns ``(err, wx, mu)``;
+    ``wx`` is updated in place like the reference."""
+    if method not in _REAL_METHODS:
+        raise ValueError("Unknown method %s" % method)
+    Ea = np.asarray(E)
+    if Ea.dtype not in _REAL_TO_CPLX:
+        raise TypeError("E must be float32 or float64, got %s" % Ea.dtype)
+    ct = _REAL_TO_CPLX[Ea.dtype]
+    rt = Ea.dtype.type
+    if Ea.ndim != 2:
+        raise ValueError("E must be 2-dimensional (modes, samples)")
+    wx_c = np.ascontiguousarray(np.asarray(wx), dtype=ct)
+    if wx_c.ndim != 3:
+        raise ValueError("wx needs to be three dimensional")
+    nmodes, L = Ea.shape
+    ntaps = wx_c.shape[-1]
+    symbols = np.ascontiguousarray(np.atleast_2d(symbols), dtype=ct)
+    assert symbols.shape[0] == nmodes, "symbols must be at least size of modes"
+    assert wx_c.shape[0] == nmodes, "wx needs to have at least as many dimensions as the maximum mode"
+    modes = np.ascontiguousarray(np.atleast_1d(modes), dtype=np.int64)
+    assert modes.max() < nmodes, "Maximum mode number must not be higher than number of modes"
+    TrSyms, Niter, os = int(TrSyms), int(Niter), int(os)
+    assert L > TrSyms * os + ntaps, "Field must be longer than the number of training symbols"
+    Ec = np.ascontiguousarray(Ea, dtype=ct)
+    err = np.zeros((nmodes, TrSyms * Niter), dtype=ct)
+    mu_io = np.array([mu], dtype=rt)
+    _lib.check(_lib.load().qb_train_equaliser_host(
+        _lib.QB_C64 if ct == np.complex64 else _lib.QB_C128, _p(Ec), nmodes, L, TrSyms, Niter, os, _p(mu_io),
+        _p(wx_c), ntaps, _p(modes), modes.size, int(bool(adaptive)), _p(symbols), symbols.shape[1],
+        _REAL_METHODS[method], int(bool(mu_shared)), _p(err)))
+    wx_r = np.ascontiguousarray(wx_c.real)
+    if isinstance(wx, np.ndarray) and wx.dtype == Ea.dtype:
+        np.copyto(wx, wx_r)            # in-place contract (:107)
+        wx_r = wx
+    return np.ascontiguousarray(err.real), wx_r, mu_io[0]

@@ -91,24 +91,59 @@ def generate_symbols_for_eq(method, M, dtype):
         return np.atleast_2d(partition_codes_complex(M)).astype(dtype)
     if method in ("sbd", "mddma", "dd"):
         return np.atleast_2d(normalised_symbols(M)).astype(dtype)
-    if method in REAL_VALUED:
-        raise NotImplementedError("real-valued equaliser methods (%s) are not part of the CUDA hot path" % method)
+    if method in ("sgncma_real", "cma_real"):          # equalisation.py:126-129 (dtype is the REAL dtype here)
+        return np.repeat([np.atleast_1d(cal_Rconstant_complex(M).real.astype(dtype))], 2, axis=0)
+    if method == "dd_real":                            # :130-133
+        symbols = normalised_symbols(M)
+        return np.vstack([symbols.real, symbols.imag]).astype(dtype)
     if method in DATA_AIDED:
         raise ValueError("%s is a data-aided method and needs the symbols to be passed" % method)
     raise ValueError("%s is unknown method" % method)
 
 
 def reshape_symbols(symbols, method, M, dtype, nmodes):
-    """Bring user symbols to (nmodes, K) (equalisation.py:568-594, complex-valued methods)."""
+    """Bring user symbols to (nmodes, K) (equalisation.py:568-594).  For the real-valued methods
+    ``nmodes`` counts the real rows (2 per polarisation) and ``dtype`` is the real dtype."""
     if symbols is None or method in NONDECISION_BASED:
         symbols = generate_symbols_for_eq(method, M, dtype)
     symbols = np.asarray(symbols)
-    if symbols.ndim == 1 or symbols.shape[0] == 1:
-        symbols = np.tile(symbols, (nmodes, 1))
-    elif symbols.shape[0] != nmodes:
-        raise ValueError("Symbols array is shape {} but signal has {} modes, symbols must be 1d or of shape "
-                         "(1, N) or ({}, N)".format(symbols.shape, nmodes, nmodes))
-    return np.atleast_2d(symbols.astype(dtype))
+    if method not in REAL_VALUED:
+        if symbols.ndim == 1 or symbols.shape[0] == 1:
+            symbols = np.tile(symbols, (nmodes, 1))
+        elif symbols.shape[0] != nmodes:
+            raise ValueError("Symbols array is shape {} but signal has {} modes, symbols must be 1d or of shape "
+                             "(1, N) or ({}, N)".format(symbols.shape, nmodes, nmodes))
+        return np.atleast_2d(symbols.astype(dtype))
+    if np.iscomplexobj(symbols):                        # :579-586
+        if symbols.ndim == 1 or symbols.shape[0] == 1:
+            symbols = np.repeat([symbols.real, symbols.imag], nmodes // 2, axis=0).squeeze()
+            symbols = symbols.reshape(nmodes, -1)
+        elif symbols.shape[0] == nmodes // 2:
+            symbols = np.vstack([symbols.real, symbols.imag])
+        else:
+            raise ValueError("Symbols array is  complex and has {} modes, but needs to either have one mode or "
+                             "the same modes as the signal ({})".format(symbols.shape[0], nmodes // 2))
+    else:                                               # :587-592
+        if symbols.shape[0] == 2 and nmodes > 2:
+            symbols = np.repeat([symbols[0], symbols[1]], nmodes // 2, axis=0).squeeze()
+            symbols = symbols.reshape(nmodes, -1)
+        elif symbols.shape[0] != nmodes:
+            raise ValueError("Symbols array is shape {} but signal has {} modes, symbols must be 1d or of shape "
+                             "(1, N) or ({}, N)".format(symbols.shape, nmodes, nmodes))
+    return symbols.astype(dtype)
+
+
+def convert_sig_to_real(E):
+    """(nmodes, L) complex -> (2*nmodes, L) real: all real parts, then all imaginary parts (equalisation.py:253-257)."""
+    Etmp = np.zeros((2 * E.shape[0], E.shape[1]), dtype=E.real.dtype)
+    Etmp[:E.shape[0]] = E.real
+    Etmp[E.shape[0]:] = E.imag
+    return np.ascontiguousarray(Etmp)
+
+
+def convert_sig_to_cmplx(E, modes, Im=np.complex128(1j)):
+    """equalisation.py:259-260"""
+    return E[:modes // 2, :] + Im * E[modes // 2:, :]
 
 
 def cal_training_symbol_len(os, ntaps, L):

@@ -137,3 +137,46 @@ def test_bps_known_answer(golden, qb):
     assert Eb.ndim == 1 and ph.ndim == 1 and ph.dtype == np.float64
     assert np.array_equal(ph, g["ph_1d"])
     assert rms(Eb - g["out_1d"]) < 1e-13
+
+
+@pytest.mark.parametrize("tag", ["c64", "c128"])
+def test_bps_twostage(golden, qb, tag):
+    """Two-stage BPS through the drop-in API: L1 index search with a per-symbol angle table (p == L) and
+    the L2 wrapper, against the vectors the reference produced."""
+    g = golden("g7_bps_twostage")
+    E, coded = g["in_" + tag], g["coded_" + tag]
+    A, N, B = int(g["A_" + tag]), int(g["N_" + tag]), int(g["B_" + tag])
+    dt = np.float32 if tag == "c64" else np.float64
+    ang = np.linspace(-np.pi / 4, np.pi / 4, A, endpoint=False, dtype=dt).reshape(1, -1)
+    assert np.array_equal(qb.dsp.bps(E[0], ang, coded, N), g["idx1_" + tag])
+    idx2 = qb.dsp.bps(E[0], g["phn_" + tag], coded, N)
+    assert idx2.dtype == np.int32 and np.array_equal(idx2, g["idx2_" + tag])
+    assert np.array_equal(qb.dsp.select_angles(g["phn_" + tag], idx2.astype(int)), g["phf_" + tag])
+    En, ph = qb.ph.bps_twostage(E, A, coded, N, B=B)
+    assert ph.dtype == dt and np.array_equal(ph, g["ph_" + tag])
+    assert rms(En - g["out_" + tag]) < (1e-6 if tag == "c64" else 1e-13)
+    with pytest.raises(ValueError):
+        qb.dsp.bps(E[0], g["phn_" + tag][:7], coded, N)          # p must be 1 or L
+
+
+@pytest.mark.parametrize("tag,tol", [("c64", 1e-5), ("c128", 1e-12)])
+@pytest.mark.parametrize("method,adaptive", [("cma_real", False), ("sgncma_real", False), ("dd_real", False),
+                                             ("dd_data_real", False), ("cma_real", True), ("dd_real", True)])
+def test_real_valued_methods(golden, qb, tag, tol, method, adaptive):
+    """equalise_signal with the REAL_VALUED methods (4x4 real MIMO, pythran_equalisation.py:80-128) through
+    the drop-in API, against the vectors the reference produced."""
+    g = golden("g8_real_valued")
+    E, M = g["E_" + tag], int(g["M_" + tag])
+    key = "%s_%s%s" % (tag, method, "_ad" if adaptive else "")
+    kw = {"symbols": g["tx_" + tag]} if method == "dd_data_real" else {}
+    Eo, wxy, err = qb.eq.equalise_signal(E, 2, 2e-3, M, Ntaps=7, method=method, apply=True,
+                                         adaptive_stepsize=adaptive, **kw)
+    assert Eo.dtype == g["out_" + key].dtype and wxy.dtype == g["wxy_" + key].dtype
+    assert err.dtype == g["err_" + key].dtype and err.shape == g["err_" + key].shape
+    assert rms(Eo - g["out_" + key]) < tol
+    assert np.max(np.abs(wxy - g["wxy_" + key])) < tol
+    # L1 seam directly: real E, real wx through apply_filter_to_signal
+    Er = np.vstack([E.real, E.imag])
+    out = qb.pe.apply_filter_to_signal(Er, 2, g["wxy_" + key], np.arange(4))
+    assert out.dtype == Er.dtype
+    assert rms((out[:2] + 1j * out[2:]) - g["out_" + key]) < tol

@@ -89,12 +89,13 @@ def test_argument_validation_before_any_cuda_work():
         pe.train_equaliser(E, 10, 1, 2, 1e-3, w, np.arange(2), False, sy, "nope")
     with pytest.raises(AssertionError):
         pe.apply_filter_to_signal(E, 0, w)
-    with pytest.raises(NotImplementedError):
-        pe.apply_filter_to_signal(E.real.copy(), 2, w)
-    with pytest.raises(NotImplementedError):
-        pe.train_equaliser_realvalued()
-    with pytest.raises(NotImplementedError):
-        dsp.bps(E[0], np.zeros((100, 8), np.float32), sy[0], 4)      # per-symbol angle table
+    with pytest.raises(TypeError):
+        pe.apply_filter_to_signal(E.real.copy(), 2, w)               # real E needs real wx (:33-36)
+    with pytest.raises(ValueError, match="Unknown method"):
+        pe.train_equaliser_realvalued(E.real.copy(), 10, 1, 2, 1e-3, w.real.copy(), np.arange(2), False,
+                                      sy.real.copy(), "mcma")
+    with pytest.raises(ValueError, match="p must be"):
+        dsp.bps(E[0], np.zeros((7, 8), np.float32), sy[0], 4)        # angle table: one row or one per symbol
     with pytest.raises(TypeError):
         pe.apply_filter_to_signal(np.zeros((2, 10), np.int32), 2, w)
 

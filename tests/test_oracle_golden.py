@@ -133,3 +133,40 @@ def test_bps_known_answer(golden):
     assert Eb.ndim == 1 and ph.ndim == 1
     assert np.array_equal(ph, g["ph_1d"])
     assert rms(Eb - g["out_1d"]) < 1e-14
+
+
+@pytest.mark.parametrize("tag", ["c64", "c128"])
+def test_bps_twostage(golden, tag):
+    """Two-stage BPS (phaserecovery.py:222-288): the per-symbol angle table form (p == L) of the index
+    search is bit exact, and so is everything built on it."""
+    g = golden("g7_bps_twostage")
+    E, coded = g["in_" + tag], g["coded_" + tag]
+    A, N, B = int(g["A_" + tag]), int(g["N_" + tag]), int(g["B_" + tag])
+    idx2 = co.bps(E[0], g["phn_" + tag], coded, N)
+    assert np.array_equal(idx2, g["idx2_" + tag])
+    assert np.array_equal(co.select_angles(g["phn_" + tag], idx2), g["phf_" + tag])
+    En, ph = co.bps_twostage_driver(E, A, coded, N, B=B)
+    assert ph.dtype == g["ph_" + tag].dtype and np.array_equal(ph, g["ph_" + tag])
+    assert rms(En - g["out_" + tag]) < (1e-6 if tag == "c64" else 1e-13)
+
+
+REAL_CASES = [("cma_real", False), ("sgncma_real", False), ("dd_real", False), ("dd_data_real", False),
+              ("cma_real", True), ("dd_real", True)]
+
+
+@pytest.mark.parametrize("tag,tol", [("c64", 5e-6), ("c128", 1e-12)])
+@pytest.mark.parametrize("method,adaptive", REAL_CASES)
+def test_real_valued_methods(golden, tag, tol, method, adaptive):
+    """equalise_signal with the REAL_VALUED methods (equalisation.py:529-565): the NumPy restatement of
+    train_equaliser_realvalued against what the reference produced."""
+    g = golden("g8_real_valued")
+    E, M = g["E_" + tag], int(g["M_" + tag])
+    key = "%s_%s%s" % (tag, method, "_ad" if adaptive else "")
+    sy = g["tx_" + tag] if method == "dd_data_real" else None
+    Eo, wxy, err = co.equalise_signal_real(E, 2, 2e-3, M, 7, method, adaptive=adaptive, symbols=sy)
+    assert wxy.dtype == g["wxy_" + key].dtype and err.dtype == g["err_" + key].dtype
+    assert Eo.dtype == g["out_" + key].dtype
+    assert rms(Eo - g["out_" + key]) < tol
+    assert np.max(np.abs(wxy - g["wxy_" + key])) < tol
+    if method != "sgncma_real":                       # sign() of a value at rounding distance from 0 may flip
+        assert rms(err - g["err_" + key]) < tol
