@@ -128,6 +128,48 @@ def equalise_signal(E, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, me
     return wxy, err
 
 
+def equalise_windows(E, starts, window, os, mu, M, Ntaps=None, TrSyms=None, Niter=1, method="mcma",
+                     adaptive_stepsize=False, symbols=None, modes=None, **kwargs):
+    """``equalise_signal(E[:, s:s + window], os, mu, M, Ntaps=Ntaps, ...)`` for every ``s`` in ``starts``, each from
+    centre-spike taps, as ONE batched launch per stage: the windows are strided views of the capture on the
+    device (one segment per window).  This is the frame search of the pilot-based receiver
+    (``pilotbased_receiver.py:395-400``: ~130 independent short trainings per capture).
+    Returns ``(wxy (nwin, nmodes, nmodes, Ntaps), err (nwin, nmodes, TrSyms*Niter))`` as NumPy arrays."""
+    starts = np.atleast_1d(np.asarray(starts, dtype=np.int64))
+    method_l = method.lower()
+    if method_l in REAL_VALUED or method_l in DATA_AIDED or starts.size < 2 or np.unique(np.diff(starts)).size > 1 \
+            or symbols is not None:
+        taps, errs = [], []
+        for s0 in starts:                       # irregular windows / per-window symbols: plain loop
+            w, e = equalise_signal(E[:, s0:s0 + window], os, mu, M, Ntaps=Ntaps, TrSyms=TrSyms, Niter=Niter,
+                                   method=method, adaptive_stepsize=adaptive_stepsize, symbols=symbols, modes=modes,
+                                   **kwargs)
+            taps.append(w)
+            errs.append(e)
+        return np.asarray(taps), np.asarray(errs)
+    method, E, nmodes, modes, wxy, _, Ntaps = _prepare(E, None, Ntaps, modes, method)
+    assert starts[-1] + window <= E.shape[1], "window beyond the end of the signal"
+    dev = _dev()
+    Ed = _to_dev(E, dev)
+    nwin, step = starts.size, int(starts[1] - starts[0])
+    Ev = Ed.as_strided((nwin, nmodes, int(window)), (step, Ed.stride(0), 1), Ed.storage_offset() + int(starts[0]))
+    wd = _to_dev(wxy, dev)[None].repeat(nwin, 1, 1, 1).contiguous()
+    rt = np.float32 if E.dtype == np.complex64 else np.float64
+    if TrSyms is None:
+        TrSyms = theory.cal_training_symbol_len(int(os), Ntaps, int(window))
+    sd = _to_dev(theory.reshape_symbols(None, method, M, E.dtype, nmodes), dev)
+    err = torch.zeros((nwin, nmodes, TrSyms * int(Niter)), dtype=Ed.dtype, device=dev)
+    mu = float(rt(mu))
+    if adaptive_stepsize and kwargs.get("mu_shared", True) and len(modes) > 1:
+        mud = torch.full((nwin, 1), mu, dtype=device._REAL[Ed.dtype], device=dev)   # one step size per window,
+        for m in modes:                                                              # carried through the modes
+            device.train_equaliser(Ev, TrSyms, int(Niter), int(os), mud, wd, [m], True, sd, method, err)
+    else:
+        mud = torch.full((nwin, len(modes)), mu, dtype=device._REAL[Ed.dtype], device=dev)
+        device.train_equaliser(Ev, TrSyms, int(Niter), int(os), mud, wd, modes, adaptive_stepsize, sd, method, err)
+    return wd.cpu().numpy(), err.cpu().numpy()
+
+
 def _equalise_signal_real(E, os, mu, M, wxy, Ntaps, TrSyms, Niter, method, adaptive_stepsize, symbols, modes,
                           apply, **kwargs):
     """equalise_signal for the real-valued methods (equalisation.py:529-565): the signal becomes 2*nmodes

@@ -8,10 +8,9 @@ Two seams:
   dual_mode_equalisation, apply_filter}`` and ``qampy.core.phaserecovery.bps`` -- the signal stays in
   HBM across train -> train -> apply.
 * ``level="l1"``: replace only the Pythran kernels the L2 code calls (``pythran_equalisation.
-  train_equaliser / apply_filter_to_signal`` by module attribute, ``phaserecovery._bps_idx_pyt /
-  select_angles`` which were from-imported at import time).  This is the parity-test seam.
-
-Real-valued methods (``*_real``) are left on the reference path.
+  train_equaliser / train_equaliser_realvalued / apply_filter_to_signal`` by module attribute,
+  ``phaserecovery._bps_idx_pyt / select_angles`` which were from-imported at import time).  This is the
+  parity-test seam; ``bps_twostage`` and the real-valued methods run through it unchanged.
 """
 import contextlib
 import importlib
@@ -36,35 +35,25 @@ def patch(level="l2"):
     ref_pe = importlib.import_module("qampy.core.equalisation.pythran_equalisation")
     if level == "l1":
         _set(ref_pe, "train_equaliser", q_pe.train_equaliser)
-        ref_apply = ref_pe.apply_filter_to_signal
-
-        def apply_filter_to_signal(E, os, wx, modes=None):
-            import numpy as np
-            if np.iscomplexobj(E) and np.iscomplexobj(wx):
-                return q_pe.apply_filter_to_signal(E, os, wx, modes)
-            return ref_apply(E, os, wx, modes)          # real-valued taps: reference path
-
-        _set(ref_pe, "apply_filter_to_signal", apply_filter_to_signal)
+        _set(ref_pe, "train_equaliser_realvalued", q_pe.train_equaliser_realvalued)
+        _set(ref_pe, "apply_filter_to_signal", q_pe.apply_filter_to_signal)
         _set(cph, "_bps_idx_pyt", q_dsp.bps)
         _set(cph, "select_angles", q_dsp.select_angles)
     elif level == "l2":
         ref = {n: getattr(ceq, n) for n in ("equalise_signal", "dual_mode_equalisation", "apply_filter")}
 
         def equalise_signal(E, os, mu, M, *args, **kwargs):
-            method = kwargs.get("method", args[4] if len(args) > 4 else "mcma")
-            if str(method).lower() in REAL_VALUED:
-                return ref["equalise_signal"](E, os, mu, M, *args, **kwargs)
             return q_eq.equalise_signal(E, os, mu, M, *args, **kwargs)
 
         def dual_mode_equalisation(E, os, mu, M, *args, **kwargs):
             methods = kwargs.get("methods", args[4] if len(args) > 4 else ("mcma", "sbd"))
             if any(str(m).lower() in REAL_VALUED for m in methods):
+                # the reference's own two-call driver (:457-464); its equalise_signal / apply_filter are ours now
                 return ref["dual_mode_equalisation"](E, os, mu, M, *args, **kwargs)
             return q_eq.dual_mode_equalisation(E, os, mu, M, *args, **kwargs)
 
         def apply_filter(E, os, wxy, method="pyt", modes=None):
-            import numpy as np
-            if method != "pyt" or not (np.iscomplexobj(E) and np.iscomplexobj(wxy)):
+            if method != "pyt":
                 return ref["apply_filter"](E, os, wxy, method=method, modes=modes)
             return q_eq.apply_filter(E, os, wxy, method=method, modes=modes)
 
@@ -80,6 +69,14 @@ def patch(level="l2"):
             return q_ph.bps(E, Mtestangles, symbols, N, method=method, **kwargs)
 
         _set(cph, "bps", bps)
+        ref_two = cph.bps_twostage
+
+        def bps_twostage(E, Mtestangles, symbols, N, B=4, method="pyt", **kwargs):
+            if method.lower() != "pyt":
+                return ref_two(E, Mtestangles, symbols, N, B=B, method=method, **kwargs)
+            return q_ph.bps_twostage(E, Mtestangles, symbols, N, B=B, method=method, **kwargs)
+
+        _set(cph, "bps_twostage", bps_twostage)
     else:
         raise ValueError("level must be 'l1' or 'l2'")
     return [name for _, name, _ in _saved]

@@ -1,0 +1,400 @@
+"""Pilot-based receiver on arrays (BASELINE config C4): frame synchronisation,
+pilot-sequence equaliser, pilot-based carrier phase and frequency offset estimation.
+
+Array-level counterparts of ``qampy/core/pilotbased_receiver.py`` (``frame_sync`` :329-434,
+``equalize_pilot_sequence`` :454-554, ``pilot_based_cpe_new`` :258-327, ``pilot_based_foe`` :32-73) and of
+the helpers they use (``phaserecovery.find_freq_offset`` / ``comp_freq_offset`` :385-473,
+``ber_functions.find_sequence_offset[_complex]`` :33-106, ``filter.moving_average`` :215-237), with the same
+argument meaning and returns, plus array forms of the signal-object methods built on them
+(``sync2frame`` / ``corr_foe`` ``signals.py:1709-1747``, ``pilot_equaliser[_nframes]``
+``qampy/equalisation.py:266-397``).
+
+What runs where: every adaptive-filter training and every FIR goes through the CUDA equaliser
+(``qampy_b200.equalisation``); the frame search trains ALL candidate windows of a capture in one batched
+launch (one segment per window, the windows being strided views of the capture), and
+``pilot_equaliser_nframes`` trains the frames that share the initial taps side by side.  What is left on
+the host is O(pilots) NumPy: correlations of a 4k-sample sequence, phase unwrap / moving average /
+interpolation of the pilot phases.
+
+``backend`` (tests only): a module-like object with ``equalise_signal``, ``apply_filter`` and optionally
+``equalise_windows``; the default is this package's CUDA path.
+"""
+import warnings
+
+import numpy as np
+
+from . import theory
+
+FRAME_SYNC_THRS = 120   # autocorrelation peak below which the sync is reported as failed (pilotbased_receiver.py:368)
+
+
+def _backend(backend):
+    if backend is not None:
+        return backend
+    from . import equalisation
+    return equalisation
+
+
+# ---------------------------------------------------------------------------------------------------------
+# small host-side helpers
+# ---------------------------------------------------------------------------------------------------------
+def find_freq_offset(sig, os=1, average_over_modes=True, fft_size=2 ** 16):
+    """Frequency offset from the peak of the spectrum of sig**4 (phaserecovery.py:385-436)."""
+    if not ((np.log2(fft_size) % 2 == 0) | (np.log2(fft_size) % 2 == 1)):
+        fft_size = 2 ** (int(np.ceil(np.log2(fft_size))))
+    sig = np.atleast_2d(sig)
+    npols = sig.shape[0]
+    spec = np.abs(np.fft.fft(sig ** 4, fft_size, axis=-1)) ** 2
+    freq_vector = np.fft.fftfreq(fft_size, 1 / os) / 4
+    freq_offset = freq_vector[np.argmax(np.abs(spec.astype(np.float64)), axis=-1)].reshape(npols, 1)
+    if average_over_modes:
+        freq_offset = np.mean(freq_offset) * np.ones(freq_offset.shape)
+    return freq_offset
+
+
+def comp_freq_offset(sig, freq_offset, os=1):
+    """Remove a frequency offset: sig * exp(-2j pi t f / os), t = 1 .. L (phaserecovery.py:438-473)."""
+    ndim = np.ndim(sig)
+    sig = np.atleast_2d(sig)
+    npols, L = sig.shape
+    t = np.arange(1, L + 1, dtype=float)
+    out = np.zeros((npols, L), dtype=sig.dtype)
+    for l in range(npols):
+        out[l] = sig[l] * np.exp(-1j * (2 * np.pi * t * freq_offset[l] / os))
+    return out.flatten() if ndim == 1 else out
+
+
+def find_sequence_offset(x, y, show_cc=False):
+    """Shift of y against x from the peak of their cross-correlation (ber_functions.py:33-72)."""
+    from scipy.signal import fftconvolve
+    X, Y = 1. * x, 1. * y
+    ac = fftconvolve(X, (Y.conj() if np.iscomplexobj(Y) else Y)[::-1], 'full')
+    idx = abs(ac).argmax() - (Y.shape[0] - 1)
+    return (idx, ac) if show_cc else idx
+
+
+def find_sequence_offset_complex(x, y):
+    """As find_sequence_offset, trying the four quarter-turn rotations of y (ber_functions.py:74-106).
+    Returns (offset, rotated y, quarter turns, correlation peak)."""
+    if not np.iscomplexobj(x) and not np.iscomplexobj(y):
+        idx, acm = find_sequence_offset(x, y, show_cc=True)
+        return idx, y, 0, acm
+    acm, ii, ix = 0., 0, 0
+    for i in range(4):
+        idx, ac = find_sequence_offset(x, y * 1.j ** i, show_cc=True)
+        act = ac.real.max()
+        if act > acm:
+            ii, ix, acm = i, idx, act
+    return ix, y * 1.j ** ii, ii, acm
+
+
+def moving_average(sig, N=3):
+    """Length-N moving average via a running sum in the signal's dtype (filter.py:215-237)."""
+    s2 = np.atleast_2d(sig)
+    ret = np.cumsum(np.insert(s2, 0, 0, axis=-1), dtype=sig.dtype, axis=-1)
+    out = (ret[:, N:] - ret[:, :-N]) / N
+    return out.flatten() if np.ndim(sig) == 1 else out
+
+
+def correct_shifts(shift_factors, ntaps, os):
+    """Frame offsets found with ntaps[0] taps, corrected for an equaliser of ntaps[1] taps (:436-443)."""
+    shift_factors = np.asarray(shift_factors)
+    if not ((ntaps[1] - ntaps[0]) % os == 0):
+        raise ValueError("Taps for search and convergence impropper configured")
+    shift_factors -= int((ntaps[1] - ntaps[0]) / 2)
+    return shift_factors
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pilot-based estimators
+# ---------------------------------------------------------------------------------------------------------
+def pilot_based_foe(rec_symbs, pilot_symbs):
+    """Frequency offset from a straight-line fit to the unwrapped pilot phase (pilotbased_receiver.py:32-73).
+    Returns (mean offset, per-mode offsets (npols, 1), fit intercepts (npols, 1))."""
+    rec_symbs, pilot_symbs = np.atleast_2d(rec_symbs), np.atleast_2d(pilot_symbs)
+    npols = rec_symbs.shape[0]
+    cond, per_mode = np.zeros([npols, 1]), np.zeros([npols, 1])
+    for l in range(npols):
+        phase = np.unwrap(np.angle(pilot_symbs[l].conj() * rec_symbs[l]))
+        fit = np.polyfit(np.arange(0, len(phase)), phase, 1)
+        per_mode[l, 0] = fit[0] / (2 * np.pi)
+        cond[l, 0] = fit[1]
+    return np.mean(per_mode), per_mode, cond
+
+
+def pilot_based_cpe_new(signal, pilot_symbs, pilot_idx, frame_len, seq_len=None, num_average=1, use_pilot_ratio=1,
+                        max_num_blocks=None, nframes=1):
+    """Carrier phase from periodically inserted pilots: unwrapped pilot phase, moving average over
+    ``num_average`` pilots, linear interpolation to every symbol, de-rotation (pilotbased_receiver.py:258-327).
+    Returns (compensated signal, phase trace), both truncated to ``nframes * frame_len``."""
+    assert num_average > 1, "need to take average over at least 3"
+    if not (num_average % 2):
+        num_average += 1
+        warnings.warn("Number of averages should be odd, adding one average, num_average={}".format(num_average))
+    signal, pilot_symbs = np.atleast_2d(signal), np.atleast_2d(pilot_symbs)
+    idx_sel = pilot_idx[:max_num_blocks:use_pilot_ratio]
+    nlen = min(frame_len * nframes, signal.shape[-1])
+    idx_full = np.ravel(np.broadcast_to(idx_sel, (nframes, idx_sel.shape[-1])) + (np.arange(nframes) * frame_len)[:, None])
+    idx_full = idx_full[idx_full < nlen]
+    rec_pilots = signal[:, idx_full]
+    pilot_symbs = np.tile(pilot_symbs[:, ::use_pilot_ratio], nframes)[:, :rec_pilots.shape[-1]]
+    assert rec_pilots.shape == pilot_symbs.shape, \
+        "Inproper pilot configuration, the number of received pilots differs from reference ones"
+    assert pilot_symbs.shape[-1] >= num_average, \
+        "Inpropper pilot symbol configuration. Larger averaging block size than total number of pilot symbols"
+    res_phase = np.unwrap(np.angle(pilot_symbs.conjugate() * rec_pilots), axis=-1)
+    res_phase_avg = moving_average(res_phase, num_average)
+    half = int((num_average - 1) / 2)
+    idx_avg = idx_full[half:-half]
+    assert idx_avg.shape[-1] == res_phase_avg.shape[-1], "averaged phase and new indices are not the same shape"
+    nmodes = pilot_symbs.shape[0]
+    trace = np.zeros((nmodes, nlen), dtype=pilot_symbs.dtype)        # the reference keeps the pilots' dtype here
+    grid = np.arange(0, nlen)
+    for i in range(nmodes):
+        trace[i] = np.interp(grid, idx_avg, res_phase_avg[i])
+    out = signal[:, :nlen] * np.exp(-1j * trace)
+    return out[:, :nframes * frame_len], trace[:, :nframes * frame_len]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# frame synchronisation
+# ---------------------------------------------------------------------------------------------------------
+def _train_windows(be, rx, starts, window, os, mu, M_pilot, Ntaps, eqargs):
+    """Taps and error of an equaliser trained from centre-spike taps on every window rx[:, s : s + window]."""
+    if hasattr(be, "equalise_windows"):
+        return be.equalise_windows(rx, starts, window, os, mu, M_pilot, Ntaps=Ntaps, **eqargs)
+    taps, errs = [], []
+    for s in starts:
+        w, e = be.equalise_signal(rx[:, s:s + window], os, mu, M_pilot, Ntaps=Ntaps, **eqargs)
+        taps.append(w)
+        errs.append(e)
+    return np.asarray(taps), np.asarray(errs)
+
+
+def frame_sync(rx_signal, ref_symbs, os, frame_len=2 ** 16, M_pilot=4, mu=1e-3, Ntaps=17, backend=None, **eqargs):
+    """Locate the pilot sequence inside a frame (pilotbased_receiver.py:329-434).
+
+    A blind equaliser (``eqargs``: method, Niter, adaptive_stepsize ...) is trained on windows of one
+    pilot-sequence length, half a window apart, over one frame; the window with the lowest error variance
+    per mode holds pilots (constant-modulus QPSK) rather than payload.  Its taps equalise a three-window
+    stretch, a coarse frequency offset is removed and the pilot sequence is located by cross-correlation,
+    which also resolves which transmitted mode each received mode carries.
+
+    Returns (shift_factor per mode, coarse frequency offset, mode_sync_order, taps of the last mode's
+    window, sync_ok)."""
+    be = _backend(backend)
+    sync_ok = True
+    rx_signal, ref_symbs = np.atleast_2d(rx_signal), np.atleast_2d(ref_symbs)
+    seq_len = ref_symbs.shape[-1]
+    nmodes = rx_signal.shape[0]
+    assert rx_signal.shape[-1] >= (frame_len + 2 * seq_len) * os, "Signal must be at least as long as frame"
+    method = eqargs.get("method")
+    if method is not None:
+        if method in theory.REAL_VALUED and np.iscomplexobj(rx_signal):
+            raise ValueError("Equaliser method is {}, but using a real-valued equaliser in frame sync is "
+                             "unsupported".format(method))
+        if method in theory.DATA_AIDED:
+            raise ValueError("Equaliser method is {}, but using a data-aided equaliser in frame sync is "
+                             "unsupported".format(method))
+    overlap = 2                                   # windows per pilot-sequence length
+    window = seq_len * os
+    step = window // overlap
+    num_steps = (frame_len * os) // step + 1      # one frame plus one extra step
+    first = overlap                               # the first window position is skipped
+    starts = np.arange(first, num_steps) * step
+    taps, errs = _train_windows(be, rx_signal, starts, window, os, mu, M_pilot, Ntaps, eqargs)
+    sub_vars = np.ones((nmodes, num_steps)) * 1e2
+    sub_vars[:, first:] = np.var(errs, axis=-1).T
+    wxys = np.zeros((num_steps, nmodes, nmodes, Ntaps), dtype=rx_signal.dtype)
+    wxys[first:] = taps
+    min_range = np.argmin(sub_vars, axis=-1)
+    mode_sync_order = np.zeros(nmodes, dtype=int)
+    shift_factor = np.zeros(nmodes, dtype=int)
+    todo = np.arange(0, nmodes)
+    foe_coarse, wx1 = None, None
+    for l in range(nmodes):
+        i_min = min_range[l]
+        long_seq = rx_signal[:, i_min * step - window:i_min * step + window]
+        wx1 = wxys[i_min]
+        symbs = be.apply_filter(long_seq, os, wx1)
+        foe_coarse = find_freq_offset(symbs)
+        symbs = comp_freq_offset(symbs, foe_coarse)
+        peak = np.zeros(nmodes, dtype=np.float64)
+        delay = np.zeros(nmodes, dtype=np.int32)
+        for ref_pol in todo:
+            ix, _, _, ac = find_sequence_offset_complex(ref_symbs[ref_pol], symbs[l])
+            delay[ref_pol], peak[ref_pol] = -ix, ac
+        best = np.argmax(peak)
+        if peak[best] < FRAME_SYNC_THRS:
+            warnings.warn("Very low autocorrelation, likely the frame-sync failed")
+            sync_ok = False
+        mode_sync_order[l] = best
+        todo = todo[todo != best]
+        shift_factor[l] = i_min * step + os * delay[best] - window
+    return shift_factor, foe_coarse, mode_sync_order, wx1, sync_ok
+
+
+def sync2frame(rx_signal, pilot_seq, os, frame_len, M_pilot=4, backend=None, **kwargs):
+    """Array form of ``SignalWithPilots.sync2frame`` (signals.py:1709-1741): frame search with the
+    reference's defaults, then the modes re-ordered to the pilots' order.
+    Returns (aligned signal, shift factors, coarse frequency offset, sync taps, sync_ok)."""
+    eqargs = {"adaptive_stepsize": True, "Niter": 10, "method": "cma", "Ntaps": 17, "mu": 5e-3}
+    eqargs.update(kwargs)
+    mu, Ntaps = eqargs.pop("mu"), eqargs.pop("Ntaps")
+    shift, foe, order, wx1, ok = frame_sync(rx_signal, pilot_seq, os, frame_len=frame_len, M_pilot=M_pilot, mu=mu,
+                                            Ntaps=Ntaps, backend=backend, **eqargs)
+    aligned = np.atleast_2d(rx_signal)[order, :]
+    shift[shift < 0] += frame_len * os
+    return aligned, shift[order], foe, wx1, ok
+
+
+def corr_foe(rx_signal, foe, os, additional_foe=0):
+    """Array form of ``SignalWithPilots.corr_foe`` (signals.py:1744-1747)."""
+    foe = np.asarray(foe)
+    return comp_freq_offset(rx_signal, np.ones(foe.shape) * (np.mean(foe) + additional_foe), os)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pilot-sequence equaliser
+# ---------------------------------------------------------------------------------------------------------
+def equalize_pilot_sequence(rx_signal, ref_symbs, shift_fctrs, os, foe_comp=False, mu=(1e-4, 1e-4), M_pilot=4,
+                            Ntaps=45, Niter=30, adaptive_stepsize=True, methods=('cma', 'cma'), wxinit=None,
+                            backend=None):
+    """Train the equaliser on the pilot sequence in two steps (pilotbased_receiver.py:454-554): ``methods[0]``
+    from ``wxinit`` (optionally followed by a pilot-based frequency offset estimate), then ``methods[0]`` and
+    ``methods[1]`` again with the pilot sequence as training symbols.  Returns (taps, frequency offsets)."""
+    be = _backend(backend)
+    rx_signal, ref_symbs = np.atleast_2d(rx_signal), np.atleast_2d(ref_symbs)
+    npols = rx_signal.shape[0]
+    seq_len = ref_symbs.shape[-1]
+    if (methods[0] in theory.REAL_VALUED) != (methods[1] in theory.REAL_VALUED):
+        raise ValueError("Using a complex and real-valued equalisation method is not supported")
+    span = seq_len * os + Ntaps - 1
+    per_mode = np.unique(shift_fctrs).shape[0] > 1
+    groups = [(shift_fctrs[i], [i]) for i in range(npols)] if per_mode else [(shift_fctrs[0], None)]
+    # step 1: blind pre-convergence (equalised pilots are only needed for the frequency offset estimate)
+    wx = wxinit
+    syms_out = np.zeros_like(ref_symbs)
+    for start, modes in groups:
+        seg = rx_signal[:, start:start + span]
+        out, wx, _ = be.equalise_signal(seg, os, mu[0], M_pilot, wxy=wx if per_mode else wxinit, Ntaps=Ntaps,
+                                        Niter=Niter, method=methods[0], adaptive_stepsize=adaptive_stepsize,
+                                        apply=True, **({"modes": modes} if modes is not None else {}))
+        if modes is None:
+            syms_out = out
+        else:
+            syms_out[modes[0]] = out
+    if foe_comp:
+        foe, foe_per_mode, _ = pilot_based_foe(syms_out, ref_symbs)
+        foe_all = np.ones(foe_per_mode.shape) * foe
+    else:
+        foe_all = np.zeros([npols, 1])
+    # step 2: both methods again, now with the pilots as training symbols
+    taps = wx.copy()
+    for start, modes in groups:
+        seg = rx_signal[:, start:start + span]
+        if foe_comp:
+            seg = comp_freq_offset(seg, foe_all, os=os)
+        kw = {"modes": modes} if modes is not None else {}
+        taps, _ = be.equalise_signal(seg, os, mu[0], M_pilot, wxy=taps, Ntaps=Ntaps, Niter=Niter, method=methods[0],
+                                     adaptive_stepsize=adaptive_stepsize, symbols=ref_symbs, apply=False, **kw)
+        # the per-mode branch of the reference passes M = 4 here (:542), the common branch M_pilot (:551)
+        taps, _ = be.equalise_signal(seg, os, mu[1], 4 if per_mode else M_pilot, wxy=taps, Ntaps=Ntaps, Niter=Niter,
+                                     method=methods[1], adaptive_stepsize=adaptive_stepsize, symbols=ref_symbs,
+                                     apply=False, **kw)
+    return np.array(taps), foe_all
+
+
+def apply_to_frames(rx_signal, wxy, shiftfctrs, os, frame_len, frames=(0,), synctaps=None, backend=None):
+    """Equalise whole frames with trained taps: array form of ``_apply_to_pilotsignal``
+    (qampy/equalisation.py:42-87).  ``shiftfctrs`` are the frame offsets found with ``synctaps`` taps."""
+    be = _backend(backend)
+    rx_signal = np.atleast_2d(rx_signal)
+    frames = list(frames)
+    Ntaps = wxy.shape[-1]
+    shifts = np.array(shiftfctrs, dtype=int)
+    if synctaps is not None and Ntaps != synctaps:
+        shifts = shifts - (Ntaps - synctaps) // 2
+    if np.min(shifts) < 0:
+        shifts += os * frame_len
+    assert shifts.max() + os * frame_len * (max(frames) + 1) < rx_signal.shape[-1] - (Ntaps - 1), \
+        "Trying to equalise frame {}, but signal is not long enough".format(max(frames))
+    per_mode = np.unique(shifts).shape[0] > 1
+    mode_groups = np.arange(wxy.shape[0]).reshape(-1, rx_signal.shape[0]).T   # real-valued taps: (re, im) rows of a mode
+    if np.all(np.diff(frames) == 1):
+        runs = [(frames[0], frames[-1] - frames[0] + 1)]      # consecutive frames: one FIR over the whole run
+    else:
+        runs = [(f, 1) for f in frames]
+    pieces = []
+    for f0, n in runs:
+        span = n * frame_len * os + Ntaps - 1
+        if per_mode:
+            rows = []
+            for mode in mode_groups:
+                i0 = shifts[mode[0]] + f0 * os * frame_len
+                rows.append(be.apply_filter(rx_signal[:, i0:i0 + span], os, wxy, modes=mode))
+            pieces.append(np.squeeze(np.array(rows)))
+        else:
+            i0 = shifts[0] + f0 * os * frame_len
+            pieces.append(be.apply_filter(rx_signal[:, i0:i0 + span], os, wxy))
+    return np.hstack(pieces) if len(pieces) > 1 else pieces[0]
+
+
+def pilot_equaliser(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps=17, apply=True,
+                    foe_comp=True, wxinit=None, frame=0, verbose=False, backend=None, **eqkwargs):
+    """Pilot-based equalisation of one frame: array form of ``qampy.equalisation.pilot_equaliser`` (:266-334).
+    ``rx_signal`` must be frame-synchronised (``sync2frame``).  Returns taps (and the equalised frame if
+    ``apply``; with ``verbose`` also the frequency offsets and ``(Ntaps, synctaps)``)."""
+    if shiftfctrs is None:
+        raise ValueError("The signal has to be synchronised to the frame first")
+    shifts = np.array(shiftfctrs, dtype=int)
+    mu = np.atleast_1d(mu)
+    if len(mu) == 1:
+        mu = np.repeat(mu, 2)
+    if wxinit is not None:
+        Ntaps = wxinit.shape[-1]
+    if (abs(Ntaps - synctaps) % 2) != 0:
+        raise ValueError("Tap difference need to be an integer of the oversampling")
+    elif Ntaps != synctaps:
+        shifts = shifts - (Ntaps - synctaps) // 2 + os * frame_len * frame
+    rx_signal = np.atleast_2d(rx_signal)
+    assert rx_signal.shape[-1] - shifts.max() > frame_len * os, \
+        "You are trying to equalise an incomplete frame which does not work"
+    taps, foe_all = equalize_pilot_sequence(rx_signal, pilot_seq, shifts, os=os, mu=mu, foe_comp=foe_comp,
+                                            Ntaps=Ntaps, wxinit=wxinit, backend=backend, **eqkwargs)
+    sig = comp_freq_offset(rx_signal, foe_all, os) if foe_comp else rx_signal
+    if not apply:
+        return (taps, foe_all, (Ntaps, synctaps)) if verbose else taps
+    eq = apply_to_frames(sig, taps, shiftfctrs, os, frame_len, frames=[frame], synctaps=synctaps, backend=backend)
+    return (taps, eq, foe_all, (Ntaps, synctaps)) if verbose else (taps, eq)
+
+
+def pilot_equaliser_nframes(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps=17, apply=True,
+                            foe_comp=True, frames=(0,), wxinit=None, backend=None, **eqkwargs):
+    """Pilot-based equalisation over several frames: array form of ``pilot_equaliser_nframes`` (:336-397).
+    Frame 0 starts from ``wxinit`` (centre spike by default); every other frame starts from frame 0's taps.
+    Returns (list of taps per frame, equalised frames stacked along time or None, list of frequency offsets)."""
+    if shiftfctrs is None:
+        raise ValueError("The signal has to be synchronised to the frame first")
+    rx_signal = np.atleast_2d(rx_signal)
+    if frames is None:
+        frames = np.arange((rx_signal.shape[-1] - np.max(shiftfctrs)) // (os * frame_len))
+    frames = np.atleast_1d(frames)
+    assert rx_signal.shape[-1] - (np.max(shiftfctrs) + np.max(frames) * frame_len * os) > frame_len * os, \
+        "The last frame must be complete for equalisation"
+    if wxinit is not None:
+        Ntaps = wxinit.shape[-1]
+    taps_all, eq_all, foe_all = [], [], []
+    for f in frames:
+        ret = pilot_equaliser(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps=synctaps,
+                              apply=apply, foe_comp=foe_comp, wxinit=wxinit, frame=int(f), verbose=True,
+                              backend=backend, **eqkwargs)
+        if f == 0:
+            wxinit = ret[0]
+        taps_all.append(ret[0])
+        if apply:
+            eq_all.append(ret[1])
+            foe_all.append(ret[2])
+        else:
+            foe_all.append(ret[1])
+    return taps_all, (np.hstack(eq_all) if apply else None), foe_all

@@ -8,6 +8,11 @@ G7  two-stage blind phase search (qampy/core/phaserecovery.py:222-288): the per-
 G8  real-valued equaliser methods (equalisation.py:529-565 -> pythran_equalisation.py:80-128):
     cma_real, sgncma_real, dd_real, dd_data_real through equalise_signal(apply=True), fixed and adaptive
     step size, c64 and c128.
+G9  pilot-based receiver on arrays (qampy/core/pilotbased_receiver.py: frame_sync :329-434,
+    equalize_pilot_sequence :454-554, pilot_based_cpe_new :258-327; phaserecovery.find_freq_offset /
+    comp_freq_offset :385-473), the recipe of test/test_equalisation.py:150-164 at reduced size:
+    dual-pol 16-QAM, frame 2**13, pilot sequence 512, one phase pilot per 32, 3 frames, SNR 25 dB,
+    DGD 10 ps, 100 MHz offset, 100 kHz linewidth, modal delay 700 samples.
 """
 import os
 import sys
@@ -68,6 +73,49 @@ def main():
             key = "%s_%s%s" % (tag, method, "_ad" if adaptive else "")
             out["out_" + key], out["wxy_" + key], out["err_" + key] = np.asarray(Eo), wxy, err
     np.savez_compressed(os.path.join(HERE, "g8_real_valued.npz"), **out)
+
+    # ---- G9: pilot-based receiver, array level ---------------------------------------------------------------
+    from qampy.core import pilotbased_receiver as pr
+    from qampy.core.equalisation import equalisation as ceq2
+    np.random.seed(91)
+    fl, sl, rat, osf = 2 ** 13, 512, 32, 2
+    sig = signals.SignalWithPilots(16, fl, sl, rat, nframes=3, nmodes=2, Mpilots=4, fb=24e9, dtype=np.complex64)
+    s2 = sig.resample(2 * sig.fb, beta=0.01)
+    s3 = impairments.simulate_transmission(s2, snr=25, dgd=10e-12, freq_off=100e6, lwdth=100e3,
+                                           modal_delay=[700, 700])
+    rx = np.array(s3)
+    pilot_seq, ph_pilots = np.array(sig.pilot_seq), np.array(sig.ph_pilots)
+    idx_pil = np.array(sig._idx_pil)
+    out = dict(rx=rx, pilot_seq=pilot_seq, ph_pilots=ph_pilots, idx_pil=idx_pil, frame_len=fl, os=osf,
+               symbols_tx=np.array(sig.symbols), coded=np.array(sig.coded_symbols), M=16)
+    # sync2frame (signals.py:1709-1741) on the array
+    sf, foe, order, wx1, ok = pr.frame_sync(rx, pilot_seq, osf, frame_len=fl, M_pilot=4, mu=5e-3, Ntaps=17,
+                                            adaptive_stepsize=True, Niter=10, method="cma")
+    out.update(fs_shift=sf.copy(), fs_foe=foe, fs_order=order, fs_wx1=wx1, fs_ok=ok)
+    rx2 = rx[order, :]
+    sf[sf < 0] += fl * osf
+    shiftf = sf[order]
+    foe_off = np.ones(foe.shape) * np.mean(foe)
+    rx3 = cph.comp_freq_offset(rx2, foe_off, osf)                       # corr_foe (signals.py:1744-1747)
+    out.update(shiftfctrs=shiftf, rx_synced_head=rx3[:, :4096])
+    # pilot_equaliser (qampy/equalisation.py:307-330) for frame 0, then apply to frame 0
+    Ntaps = 45
+    eq_shift = shiftf - (Ntaps - 17) // 2
+    for tag, methods in (("sbd", ("cma", "sbd")), ("data", ("cma", "sbd_data"))):
+        taps, foe_all = pr.equalize_pilot_sequence(rx3, pilot_seq, eq_shift, os=osf, mu=(1e-3, 1e-3), foe_comp=False,
+                                                   Ntaps=Ntaps, methods=methods)
+        out.update({"taps_" + tag: taps, "foe_all_" + tag: foe_all})
+    taps = out["taps_sbd"]
+    i0 = eq_shift[0]
+    eq = ceq2.apply_filter(rx3[:, i0:i0 + fl * osf + Ntaps - 1], osf, taps)
+    out.update(eq_frame0=np.asarray(eq))
+    idx = np.nonzero(idx_pil)[0][sl:]
+    cpe, trace = pr.pilot_based_cpe_new(eq, ph_pilots, idx, fl, seq_len=None, max_num_blocks=None,
+                                        use_pilot_ratio=1, num_average=5, nframes=1)
+    out.update(cpe_out=np.asarray(cpe), cpe_trace=trace)
+    foe_p, foe_pm, cond = pr.pilot_based_foe(np.asarray(eq)[:, :sl], pilot_seq)
+    out.update(pfoe=foe_p, pfoe_mode=foe_pm, pfoe_cond=cond)
+    np.savez_compressed(os.path.join(HERE, "g9_pilot_rx.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))
