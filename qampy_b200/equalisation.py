@@ -128,46 +128,108 @@ def equalise_signal(E, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, me
     return wxy, err
 
 
-def equalise_windows(E, starts, window, os, mu, M, Ntaps=None, TrSyms=None, Niter=1, method="mcma",
-                     adaptive_stepsize=False, symbols=None, modes=None, **kwargs):
-    """``equalise_signal(E[:, s:s + window], os, mu, M, Ntaps=Ntaps, ...)`` for every ``s`` in ``starts``, each from
-    centre-spike taps, as ONE batched launch per stage: the windows are strided views of the capture on the
-    device (one segment per window).  This is the frame search of the pilot-based receiver
-    (``pilotbased_receiver.py:395-400``: ~130 independent short trainings per capture).
-    Returns ``(wxy (nwin, nmodes, nmodes, Ntaps), err (nwin, nmodes, TrSyms*Niter))`` as NumPy arrays."""
+def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, method="mcma",
+                     adaptive_stepsize=False, symbols=None, modes=None, apply=False, **kwargs):
+    """``equalise_signal(E[:, s:s + window], os, mu, M, wxy=..., ...)`` for every ``s`` in ``starts`` as ONE batched
+    launch per stage: the windows are strided views of the capture on the device, one segment per window.
+
+    This is how the pilot-based receiver maps onto the GPU: the frame search trains
+    ~130 candidate windows of a capture (``pilotbased_receiver.py:395-400``) and the pilot equaliser trains
+    every frame's pilot sequence from the same initial taps (``qampy/equalisation.py:384-389``) -- short,
+    independent, serial trainings that only fill the machine side by side.
+
+    ``E``: NumPy array or CUDA tensor (nmodes, L).  ``wxy``: None (centre spike), (nmodes, nmodes, Ntaps)
+    shared by all windows, or (nwin, nmodes, nmodes, Ntaps).  ``symbols``: as for ``equalise_signal``, shared
+    by all windows.  Returns ``(wxy (nwin, nmodes, nmodes, Ntaps), err (nwin, nmodes, TrSyms*Niter))`` and, with
+    ``apply``, the equalised windows ``(nwin, len(modes), (window - Ntaps + 1)//os)`` first -- NumPy arrays."""
     starts = np.atleast_1d(np.asarray(starts, dtype=np.int64))
     method_l = method.lower()
-    if method_l in REAL_VALUED or method_l in DATA_AIDED or starts.size < 2 or np.unique(np.diff(starts)).size > 1 \
-            or symbols is not None:
-        taps, errs = [], []
-        for s0 in starts:                       # irregular windows / per-window symbols: plain loop
-            w, e = equalise_signal(E[:, s0:s0 + window], os, mu, M, Ntaps=Ntaps, TrSyms=TrSyms, Niter=Niter,
-                                   method=method, adaptive_stepsize=adaptive_stepsize, symbols=symbols, modes=modes,
-                                   **kwargs)
-            taps.append(w)
-            errs.append(e)
-        return np.asarray(taps), np.asarray(errs)
-    method, E, nmodes, modes, wxy, _, Ntaps = _prepare(E, None, Ntaps, modes, method)
-    assert starts[-1] + window <= E.shape[1], "window beyond the end of the signal"
+    if method_l in REAL_VALUED or starts.size < 2 or np.unique(np.diff(starts)).size > 1:
+        outs, taps, errs = [], [], []
+        Eh = E.cpu().numpy() if torch.is_tensor(E) else np.asarray(E)
+        for k, s0 in enumerate(starts):         # irregular windows / real-valued methods: plain loop
+            w0 = None if wxy is None else (wxy[k] if np.ndim(wxy) == 4 else wxy)
+            ret = equalise_signal(Eh[:, s0:s0 + window], os, mu, M, wxy=None if w0 is None else np.array(w0),
+                                  Ntaps=Ntaps, TrSyms=TrSyms, Niter=Niter, method=method,
+                                  adaptive_stepsize=adaptive_stepsize, symbols=symbols, modes=modes, apply=apply,
+                                  **kwargs)
+            if apply:
+                outs.append(ret[0])
+            taps.append(ret[-2])
+            errs.append(ret[-1])
+        res = (np.asarray(taps), np.asarray(errs))
+        return (np.asarray(outs),) + res if apply else res
     dev = _dev()
-    Ed = _to_dev(E, dev)
+    if torch.is_tensor(E):
+        Ed = E if E.is_cuda else E.to(dev)
+        cdtype = np.dtype(np.complex64 if Ed.dtype == torch.complex64 else np.complex128)
+    else:
+        Eh = np.atleast_2d(_check_complex(E))
+        cdtype = Eh.dtype
+        Ed = _to_dev(Eh, dev)
+    if method_l not in _lib.METHODS:
+        raise ValueError("Unknown method %s" % method)
+    nmodes, L = Ed.shape
+    modes = np.arange(nmodes) if modes is None else np.atleast_1d(modes)
+    assert np.max(modes) < nmodes, "largest mode number is larger than shape of signal"
     nwin, step = starts.size, int(starts[1] - starts[0])
+    assert starts[0] >= 0 and starts[-1] + window <= L, "window beyond the end of the signal"
+    if wxy is None:
+        w0 = theory.init_taps(Ntaps, nmodes, cdtype)
+    else:
+        w0 = np.ascontiguousarray(wxy, dtype=cdtype)
+        Ntaps = w0.shape[-1]
+        assert w0.shape[-3:] == (nmodes, nmodes, Ntaps), "wxy must be (nmodes, nmodes, Ntaps) per window"
+    wd = _to_dev(w0, dev)
+    wd = (wd[None].repeat(nwin, 1, 1, 1) if wd.dim() == 3 else wd).contiguous()
+    assert wd.shape[0] == nwin, "one set of initial taps per window expected"
     Ev = Ed.as_strided((nwin, nmodes, int(window)), (step, Ed.stride(0), 1), Ed.storage_offset() + int(starts[0]))
-    wd = _to_dev(wxy, dev)[None].repeat(nwin, 1, 1, 1).contiguous()
-    rt = np.float32 if E.dtype == np.complex64 else np.float64
+    rt = np.float32 if cdtype == np.complex64 else np.float64
     if TrSyms is None:
         TrSyms = theory.cal_training_symbol_len(int(os), Ntaps, int(window))
-    sd = _to_dev(theory.reshape_symbols(None, method, M, E.dtype, nmodes), dev)
+    sd = _to_dev(theory.reshape_symbols(symbols, method_l, M, cdtype.type, nmodes), dev)
     err = torch.zeros((nwin, nmodes, TrSyms * int(Niter)), dtype=Ed.dtype, device=dev)
     mu = float(rt(mu))
     if adaptive_stepsize and kwargs.get("mu_shared", True) and len(modes) > 1:
         mud = torch.full((nwin, 1), mu, dtype=device._REAL[Ed.dtype], device=dev)   # one step size per window,
         for m in modes:                                                              # carried through the modes
-            device.train_equaliser(Ev, TrSyms, int(Niter), int(os), mud, wd, [m], True, sd, method, err)
+            device.train_equaliser(Ev, TrSyms, int(Niter), int(os), mud, wd, [m], True, sd, method_l, err)
     else:
         mud = torch.full((nwin, len(modes)), mu, dtype=device._REAL[Ed.dtype], device=dev)
-        device.train_equaliser(Ev, TrSyms, int(Niter), int(os), mud, wd, modes, adaptive_stepsize, sd, method, err)
-    return wd.cpu().numpy(), err.cpu().numpy()
+        device.train_equaliser(Ev, TrSyms, int(Niter), int(os), mud, wd, modes, adaptive_stepsize, sd, method_l, err)
+    res = (wd.cpu().numpy(), err.cpu().numpy())
+    if apply:
+        out = device.apply_filter_to_signal(Ev, int(os), wd, modes)
+        return (out.cpu().numpy(),) + res
+    return res
+
+
+def apply_windows(E, starts, window, os, wxy, modes=None):
+    """``apply_filter(E[:, s:s + window], os, wxy[k])`` for every window k as one launch (per-window taps
+    ``wxy`` (nwin, nmodes, nmodes, Ntaps), or one shared set).  Returns (nwin, len(modes), (window-Ntaps+1)//os)."""
+    starts = np.atleast_1d(np.asarray(starts, dtype=np.int64))
+    dev = _dev()
+    if torch.is_tensor(E):
+        Ed = E if E.is_cuda else E.to(dev)
+        cdtype = np.dtype(np.complex64 if Ed.dtype == torch.complex64 else np.complex128)
+    else:
+        Eh = np.atleast_2d(_check_complex(E))
+        cdtype = Eh.dtype
+        Ed = _to_dev(Eh, dev)
+    nmodes, L = Ed.shape
+    w = np.ascontiguousarray(wxy, dtype=cdtype)
+    nwin = starts.size
+    wd = _to_dev(w, dev)
+    wd = (wd[None].repeat(nwin, 1, 1, 1) if wd.dim() == 3 else wd).contiguous()
+    modes = np.arange(w.shape[-3]) if modes is None else np.atleast_1d(modes)
+    assert starts[0] >= 0 and starts.max() + window <= L, "window beyond the end of the signal"
+    if nwin > 1 and np.unique(np.diff(starts)).size == 1 and starts[1] > starts[0]:
+        Ev = Ed.as_strided((nwin, nmodes, int(window)), (int(starts[1] - starts[0]), Ed.stride(0), 1),
+                           Ed.storage_offset() + int(starts[0]))
+        return device.apply_filter_to_signal(Ev, int(os), wd, modes).cpu().numpy()
+    outs = [device.apply_filter_to_signal(Ed[None, :, int(s0):int(s0) + int(window)], int(os), wd[k:k + 1], modes)[0]
+            for k, s0 in enumerate(starts)]
+    return torch.stack(outs).cpu().numpy()
 
 
 def _equalise_signal_real(E, os, mu, M, wxy, Ntaps, TrSyms, Niter, method, adaptive_stepsize, symbols, modes,

@@ -369,13 +369,71 @@ def pilot_equaliser(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, 
     return (taps, eq, foe_all, (Ntaps, synctaps)) if verbose else (taps, eq)
 
 
+def _pilot_frames_batched(be, rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps, frames, wxinit,
+                          apply, M_pilot=4, Niter=30, adaptive_stepsize=True, methods=('cma', 'cma')):
+    """equalize_pilot_sequence + apply for several frames that start from the SAME initial taps, without
+    frequency offset estimation: every training stage is one batched launch over the frames (one segment
+    per frame, strided views of the capture).  Frame f gives what ``pilot_equaliser(frame=f)`` gives."""
+    ref = np.atleast_2d(pilot_seq)
+    npols = rx_signal.shape[0]
+    frames = np.asarray(frames, dtype=np.int64)
+    shifts = np.array(shiftfctrs, dtype=int)
+    train_shifts = shifts - (Ntaps - synctaps) // 2 if Ntaps != synctaps else shifts.copy()
+    # the reference adds the frame offset to the training window only when Ntaps != synctaps (:316-317)
+    foff = os * frame_len * frames if Ntaps != synctaps else 0 * frames
+    assert rx_signal.shape[-1] - (train_shifts.max() + foff.max()) > frame_len * os, \
+        "You are trying to equalise an incomplete frame which does not work"
+    if (methods[0] in theory.REAL_VALUED) != (methods[1] in theory.REAL_VALUED):
+        raise ValueError("Using a complex and real-valued equalisation method is not supported")
+    span = ref.shape[-1] * os + Ntaps - 1
+    per_mode = np.unique(train_shifts).shape[0] > 1
+    groups = [(train_shifts[i], [i]) for i in range(npols)] if per_mode else [(train_shifts[0], None)]
+    wx = wxinit
+    for start, modes in groups:                 # step 1: blind pre-convergence from the initial taps
+        wx, _ = be.equalise_windows(rx_signal, start + foff, span, os, mu[0], M_pilot,
+                                    wxy=wx if per_mode else wxinit, Ntaps=Ntaps, Niter=Niter, method=methods[0],
+                                    adaptive_stepsize=adaptive_stepsize, modes=modes)
+    taps = wx
+    for start, modes in groups:                 # step 2: both methods with the pilot sequence as training symbols
+        taps, _ = be.equalise_windows(rx_signal, start + foff, span, os, mu[0], M_pilot, wxy=taps, Ntaps=Ntaps,
+                                      Niter=Niter, method=methods[0], adaptive_stepsize=adaptive_stepsize,
+                                      symbols=ref, modes=modes)
+        taps, _ = be.equalise_windows(rx_signal, start + foff, span, os, mu[1], 4 if per_mode else M_pilot, wxy=taps,
+                                      Ntaps=Ntaps, Niter=Niter, method=methods[1],
+                                      adaptive_stepsize=adaptive_stepsize, symbols=ref, modes=modes)
+    if not apply:
+        return taps, None
+    ashifts = shifts - (Ntaps - synctaps) // 2 if Ntaps != synctaps else shifts.copy()
+    if np.min(ashifts) < 0:
+        ashifts += os * frame_len
+    aspan = frame_len * os + Ntaps - 1
+    assert ashifts.max() + os * frame_len * (frames.max() + 1) < rx_signal.shape[-1] - (Ntaps - 1), \
+        "Trying to equalise frame {}, but signal is not long enough".format(frames.max())
+    if np.unique(ashifts).shape[0] > 1:
+        mode_groups = np.arange(taps.shape[-3]).reshape(-1, npols).T
+        rows = [be.apply_windows(rx_signal, ashifts[mode[0]] + os * frame_len * frames, aspan, os, taps, modes=mode)
+                for mode in mode_groups]
+        eq = np.concatenate(rows, axis=1)       # (nframes, nmodes, frame_len)
+    else:
+        eq = be.apply_windows(rx_signal, ashifts[0] + os * frame_len * frames, aspan, os, taps)
+    return taps, eq
+
+
 def pilot_equaliser_nframes(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps=17, apply=True,
-                            foe_comp=True, frames=(0,), wxinit=None, backend=None, **eqkwargs):
+                            foe_comp=True, frames=(0,), wxinit=None, backend=None, batched=True, **eqkwargs):
     """Pilot-based equalisation over several frames: array form of ``pilot_equaliser_nframes`` (:336-397).
-    Frame 0 starts from ``wxinit`` (centre spike by default); every other frame starts from frame 0's taps.
+    Frame 0 starts from ``wxinit`` (centre spike by default); every frame after it starts from frame 0's taps
+    -- those frames are independent of one another and, without frequency offset estimation, are trained and
+    filtered side by side (``batched``; one launch per stage for all of them).
+
+    ``batched=False`` is the reference's loop as it actually behaves: its ``wxinit`` array is trained in place
+    by every call (``equalisation.py:547``), so frame f warm-starts from frame f-1's pre-convergence taps
+    rather than from frame 0's.  ``batched=True`` (default) is what that loop reads like -- every frame from
+    frame 0's taps -- and frame f then equals ``pilot_equaliser(frame=f, wxinit=<copy of frame 0's taps>)``.
     Returns (list of taps per frame, equalised frames stacked along time or None, list of frequency offsets)."""
     if shiftfctrs is None:
         raise ValueError("The signal has to be synchronised to the frame first")
+    be = _backend(backend)
     rx_signal = np.atleast_2d(rx_signal)
     if frames is None:
         frames = np.arange((rx_signal.shape[-1] - np.max(shiftfctrs)) // (os * frame_len))
@@ -384,8 +442,25 @@ def pilot_equaliser_nframes(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu,
         "The last frame must be complete for equalisation"
     if wxinit is not None:
         Ntaps = wxinit.shape[-1]
+    mu2 = np.atleast_1d(mu)
+    mu2 = np.repeat(mu2, 2) if len(mu2) == 1 else mu2
     taps_all, eq_all, foe_all = [], [], []
-    for f in frames:
+    k = 0
+    while k < len(frames):
+        # frames up to and including frame 0 one at a time (frame 0 redefines the initial taps, :386-387) ...
+        rest = frames[k:]
+        if batched and not foe_comp and hasattr(be, "equalise_windows") and len(rest) > 1 and 0 not in rest \
+                and (abs(Ntaps - synctaps) % 2) == 0:
+            # ... everything after it in one batch
+            taps, eq = _pilot_frames_batched(be, rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu2, Ntaps, synctaps,
+                                             rest, wxinit, apply, **eqkwargs)
+            for j in range(len(rest)):
+                taps_all.append(taps[j])
+                foe_all.append(np.zeros([rx_signal.shape[0], 1]))
+                if apply:
+                    eq_all.append(eq[j])
+            break
+        f = frames[k]
         ret = pilot_equaliser(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps=synctaps,
                               apply=apply, foe_comp=foe_comp, wxinit=wxinit, frame=int(f), verbose=True,
                               backend=backend, **eqkwargs)
@@ -397,4 +472,5 @@ def pilot_equaliser_nframes(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu,
             foe_all.append(ret[2])
         else:
             foe_all.append(ret[1])
+        k += 1
     return taps_all, (np.hstack(eq_all) if apply else None), foe_all

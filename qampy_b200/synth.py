@@ -38,10 +38,28 @@ def synth_signal(M, nsym, nmodes=2, os=2, beta=0.1, snr_db=28.0, theta=math.pi /
     alphabet = torch.from_numpy(normalised_symbols(M)).to(device)
     idx = torch.randint(0, M, (nmodes, nsym), generator=gen, device=device)
     syms = alphabet[idx]
+    return shape_and_impair(syms, os, beta, snr_db, theta, dgd, fb, linewidth, seed, gen, dtype)
+
+
+def shape_and_impair(syms, os=2, beta=0.1, snr_db=28.0, theta=math.pi / 5.6, dgd=40e-12, fb=40e9, linewidth=None,
+                     seed=0, gen=None, dtype=torch.complex64, freq_off=None, tx_linewidth=None):
+    """Pulse shaping and channel for given symbols (nmodes, nsym): RRC to ``os`` samples per symbol, PMD, AWGN,
+    optional frequency offset (Hz) and Wiener phase noise -- ``linewidth`` on the received rows (after the
+    polarisation mixing), ``tx_linewidth`` on the transmitted polarisations before it, which is where the
+    reference's ``simulate_transmission`` puts it (``impairments.py:159-160`` before ``apply_PMD``).
+    Returns (E, syms)."""
+    device = syms.device
+    nmodes, nsym = syms.shape
+    if gen is None:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(int(seed) + 17)
     n = nsym * os
     x = torch.zeros((nmodes, n), dtype=torch.complex128, device=device)
     x[:, ::os] = syms
     X = torch.fft.fft(x, dim=1) * _rrc_freq(n, os, beta, device)
+    if tx_linewidth:
+        x = apply_phase_noise(torch.fft.ifft(X, dim=1), tx_linewidth, os * fb, seed=seed + 2)
+        X = torch.fft.fft(x.to(torch.complex128), dim=1)
     if nmodes == 2 and theta is not None:
         # first-order PMD: rotate, delay the axes by +-dgd/2, rotate back
         omega = 2 * math.pi * torch.fft.fftfreq(n, d=1.0 / (os * fb), device=device, dtype=torch.float64)
@@ -57,9 +75,48 @@ def synth_signal(M, nsym, nmodes=2, os=2, beta=0.1, snr_db=28.0, theta=math.pi /
         sigma = math.sqrt(os) * 10 ** (-snr_db / 20)
         noise = torch.randn((nmodes, n, 2), generator=gen, device=device, dtype=torch.float64)
         x = x + sigma / math.sqrt(2) * torch.view_as_complex(noise)
+    if freq_off:
+        t = torch.arange(n, device=device, dtype=torch.float64)
+        x = x * torch.exp(2j * math.pi * freq_off / (os * fb) * t)
     if linewidth:
         x = apply_phase_noise(x, linewidth, os * fb, seed=seed + 1)
     return x.to(dtype), syms.to(dtype)
+
+
+def synth_pilot_signal(M, frame_len, pilot_seq_len, pilot_ins_rat, nframes, nmodes=2, Mpilots=4, os=2, beta=0.01,
+                       snr_db=30.0, theta=math.pi / 3.731, dgd=10e-12, fb=24e9, freq_off=None, linewidth=None,
+                       delay=0, seed=0, dtype=torch.complex64, device="cpu"):
+    """Pilot-framed signal for the pilot-based receiver (BASELINE config C4; the layout of the reference's
+    ``SignalWithPilots``): every frame starts with a ``pilot_seq_len`` QPSK pilot sequence, after it every
+    ``pilot_ins_rat``-th symbol is a phase pilot, the rest is M-QAM payload; pilots are the same in every
+    frame, payload is not.  ``delay`` rolls the signal by that many samples (unknown frame start).
+    Returns a dict: E (nmodes, nframes*frame_len*os), symbols (nmodes, nframes*frame_len), pilot_seq
+    (nmodes, pilot_seq_len), ph_pilots (nmodes, n_ph), idx_pil (frame_len,) bool."""
+    device = torch.device(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    assert (frame_len - pilot_seq_len) % pilot_ins_rat == 0
+    idx_pil = np.zeros(frame_len, dtype=bool)
+    idx_pil[:pilot_seq_len] = True
+    idx_pil[pilot_seq_len::pilot_ins_rat] = True
+    npil = int(idx_pil.sum())
+    pal = torch.from_numpy(normalised_symbols(Mpilots)).to(device)
+    dal = torch.from_numpy(normalised_symbols(M)).to(device)
+    pilots = pal[torch.randint(0, Mpilots, (nmodes, npil), generator=gen, device=device)]
+    frames = []
+    mask = torch.from_numpy(idx_pil).to(device)
+    for _ in range(nframes):
+        fr = torch.empty((nmodes, frame_len), dtype=torch.complex128, device=device)
+        fr[:, mask] = pilots
+        fr[:, ~mask] = dal[torch.randint(0, M, (nmodes, frame_len - npil), generator=gen, device=device)]
+        frames.append(fr)
+    syms = torch.cat(frames, dim=1)
+    E, _ = shape_and_impair(syms, os, beta, snr_db, theta, dgd, fb, None, seed, gen, dtype, freq_off,
+                            tx_linewidth=linewidth)
+    if delay:
+        E = torch.roll(E, int(delay), dims=1)
+    return dict(E=E, symbols=syms.to(dtype), pilot_seq=pilots[:, :pilot_seq_len].to(dtype),
+                ph_pilots=pilots[:, pilot_seq_len:].to(dtype), idx_pil=idx_pil)
 
 
 def apply_phase_noise(x, linewidth, fs, seed=0):
