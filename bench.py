@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--seg", type=int, default=-1,
                     help="output symbols per segment; -1 = smallest length >= 8192 that fills whole GPU waves "
                          "(pipeline.balanced_segment_symbols), 0 = one segment")
-    ap.add_argument("--chunks", type=int, default=12, help="host<->device overlap chunks of the e2e path")
+    ap.add_argument("--chunks", type=int, default=8, help="host<->device overlap chunks of the e2e path")
     ap.add_argument("--ntaps", type=int, default=45)
     ap.add_argument("--M", type=int, default=64)
     ap.add_argument("--angles", type=int, default=64)

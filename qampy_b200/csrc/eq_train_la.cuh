@@ -98,15 +98,21 @@ __device__ __forceinline__ void tile_gram(const float *tile, int nslots, int nmo
 }
 
 template <int LPS, int NQ, int METHOD, int NMASK>
-__global__ void __launch_bounds__(32) train_la_kernel(TrainParams<float> p, FastGeom g)
+__global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<float> p, FastGeom g, int warp_smem)
 {
     static_assert(NQ % 2 == 0, "NQ must be even (os = 2: the window moves by one pair per symbol)");
     constexpr int NP = NQ / 2;     // pairs per lane
     constexpr int B = NP + 2;      // circular pair window: symbols i-1 .. i+1; also symbols per unrolled chunk
     constexpr int GPW = 32 / LPS;  // streams (lane groups) per warp
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x, grp = lane / LPS, gl = lane % LPS;
-    const long long stream0 = (long long)blockIdx.x * GPW;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    // TRAIN_WPB independent warps per CTA, each with its own slice of shared memory and its own streams (no
+    // block-level synchronisation anywhere): see launch geometry below
+    const int wib = threadIdx.x >> 5;
+    const long long wblk = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (wblk * GPW >= p.nstreams) return;
+    unsigned char *smem_raw = smem_all + (size_t)wib * warp_smem;
+    const int lane = threadIdx.x & 31, grp = lane / LPS, gl = lane % LPS;
+    const long long stream0 = wblk * GPW;
     const bool active = stream0 + grp < p.nstreams;
     const long long stream = active ? stream0 + grp : p.nstreams - 1;
     const long long seg = stream / p.nsel;
@@ -343,7 +349,7 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     smem = ((size_t)2 * g.nslots * p.nmodes * g.pitch + (size_t)g.nslots * g.tile_syms +
             (size_t)g.nslots * (32 * GRAM_CH + 1) + (size_t)GPW * g.tile_syms + (size_t)GPW * p.nsym_smem) *
            sizeof(float2);
-    if (smem > 64 * 1024) return 0;
+    if (smem > 56 * 1024) return 0;   // four warp slices per CTA must fit 227 kB
     return nq;
 }
 
@@ -354,11 +360,13 @@ static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem
     static bool attr_done = false;
     if (!attr_done) {
         QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     const long long nblk = (p.nstreams + GPW - 1) / GPW;
-    train_la_kernel<LPS, NQ, METHOD, NMASK><<<(unsigned)nblk, 32, smem, st>>>(p, g);
+    const size_t wsm = (smem + 15) & ~(size_t)15;   // per-warp slice, 16-byte aligned
+    const int wpb = (int)(train_warps_per_cta(nblk) < nblk ? train_warps_per_cta(nblk) : nblk);   // never more warps (or shared memory) than streams need
+    train_la_kernel<LPS, NQ, METHOD, NMASK><<<(unsigned)((nblk + wpb - 1) / wpb), 32 * wpb, wpb * wsm, st>>>(p, g, (int)wsm);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
