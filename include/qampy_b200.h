@@ -158,6 +158,21 @@ int qb_bps_rows_host(int dtype, const void *E, int64_t nstream, int64_t L, const
 int qb_detect_grid_host(int dtype, const void *symbols, int64_t M, void *lev_re, int64_t *n_re,
                         void *lev_im, int64_t *n_im);
 
+/* ---- element-wise stages of the pilot-based receiver (device pointers only) ----------------------
+ * qb_freq_shift_dev: comp_freq_offset, qampy/core/phaserecovery.py:438-473:
+ *     out[r, t] = E[r, t] * exp(-2j*pi*(t0 + t + 1)*freq[r]/os),  freq (nrows) float64 on the device;
+ *     t0 = 0 for a whole signal, the window's first sample index when only a window is compensated.
+ * qb_pilot_cpe_dev: pilot_based_cpe_new, qampy/core/pilotbased_receiver.py:258-327, one frame per row:
+ *     pilot_idx (npilots) int64 sorted positions inside the row, pilots (nrows, npilots) reference pilots at
+ *     pilots + r*pilot_stride; residual pilot phase -> unwrap -> moving average over num_average (odd) ->
+ *     linear interpolation to every symbol -> out = E*exp(-1j*phase); trace (real, optional) = phase.     */
+int qb_freq_shift_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, const double *freq,
+                      int64_t os, int64_t t0, void *out, int64_t out_stride, void *stream);
+int qb_pilot_cpe_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t nlen,
+                     const int64_t *pilot_idx, const void *pilots, int64_t pilot_stride, int64_t npilots,
+                     int64_t num_average, void *out, int64_t out_stride, void *trace, int64_t trace_stride,
+                     void *stream);
+
 /* ---- select_angles(angles, idx): out[i] = angles[p > 1 ? i : 0][idx[i]] ----------------------- */
 int qb_select_angles_dev(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
                          int64_t L, void *out, void *stream);

@@ -38,6 +38,8 @@ PROTOTYPES = {
                          _vp, _vp, _vp, _vp], _int),
     "qb_bps_rows_host": ([_int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp], _int),
     "qb_detect_grid_host": ([_int, _vp, _i64, _vp, _vp, _vp, _vp], _int),
+    "qb_freq_shift_dev": ([_int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp], _int),
+    "qb_pilot_cpe_dev": ([_int, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp], _int),
     "qb_select_angles_dev": ([_int, _vp, _i64, _i64, _vp, _i64, _vp, _vp], _int),
     "qb_select_angles_host": ([_int, _vp, _i64, _i64, _vp, _i64, _vp], _int),
 }

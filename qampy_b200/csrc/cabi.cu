@@ -40,6 +40,12 @@ int bps_dispatch(int dtype, const void *E, int64_t nstream, int64_t stream_strid
 int select_angles_dispatch(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
                            int64_t L, void *out, cudaStream_t st);
 
+int freq_shift_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, const double *freq,
+                        int64_t os, int64_t t0, void *out, int64_t out_stride, cudaStream_t st);
+int pilot_cpe_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t nlen, const int64_t *pidx,
+                       const void *pilots, int64_t pilot_stride, int64_t nph, int64_t navg, void *out,
+                       int64_t out_stride, void *trace, int64_t trace_stride, cudaStream_t st);
+
 static inline size_t csize(int dtype) { return dtype == QB_C64 ? 8 : 16; }
 static inline size_t rsize(int dtype) { return dtype == QB_C64 ? 4 : 8; }
 
@@ -419,6 +425,29 @@ static int bps_host_impl(int dtype, const void *E, int64_t nstream, int64_t L, c
     if (Eout) QB_CUDA_CHECK(cudaMemcpyAsync(Eout, dO.p, nE * cs, cudaMemcpyDeviceToHost, st));
     QB_CUDA_CHECK(cudaStreamSynchronize(st));
     return QB_OK;
+}
+
+int qb_freq_shift_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, const double *freq,
+                      int64_t os, int64_t t0, void *out, int64_t out_stride, void *stream)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(nrows >= 0 && L >= 0 && os >= 1 && t0 >= 0, "invalid sizes");
+    QB_REQUIRE(nrows == 0 || L == 0 || (E && freq && out), "E, freq and out must not be NULL");
+    QB_REQUIRE(nrows <= 65535, "at most 65535 rows");
+    return freq_shift_dispatch(dtype, E, nrows, row_stride, L, freq, os, t0, out, out_stride, (cudaStream_t)stream);
+}
+
+int qb_pilot_cpe_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t nlen, const int64_t *pilot_idx,
+                     const void *pilots, int64_t pilot_stride, int64_t npilots, int64_t num_average, void *out,
+                     int64_t out_stride, void *trace, int64_t trace_stride, void *stream)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(nrows >= 0 && nlen >= 0, "invalid sizes");
+    QB_REQUIRE(num_average > 1 && (num_average % 2) == 1, "num_average must be odd and at least 3");
+    QB_REQUIRE(npilots >= num_average, "Larger averaging block size than total number of pilot symbols");
+    QB_REQUIRE(nrows == 0 || nlen == 0 || (E && pilot_idx && pilots && out), "E, pilot_idx, pilots and out must not be NULL");
+    return pilot_cpe_dispatch(dtype, E, nrows, row_stride, nlen, pilot_idx, pilots, pilot_stride, npilots, num_average,
+                              out, out_stride, trace, trace_stride, (cudaStream_t)stream);
 }
 
 int qb_select_angles_dev(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx, int64_t L,

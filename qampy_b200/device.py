@@ -128,3 +128,39 @@ def bps(E, tables, N, want_idx=True, want_ph=True, want_out=True, use_slicer=Tru
         _ptr(tables.symbols), tables.M, _ptr(tables.lev_re), n_re, _ptr(tables.lev_im), n_im, int(N),
         _ptr(idx), _ptr(ph), _ptr(out), _stream()))
     return out, ph, idx
+
+
+def freq_shift(E, freq, os, t0=0, out=None):
+    """``comp_freq_offset`` (phaserecovery.py:438-473) on the device: ``out[r, t] = E[r, t] * exp(-2j pi (t0+t+1)
+    freq[r] / os)`` for every row of ``E`` (nrows, L); ``freq`` one value per row (float64)."""
+    _check_cuda(E, out)
+    assert E.dim() == 2 and E.stride(1) == 1
+    nrows, L = E.shape
+    f = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(freq, dtype=np.float64).reshape(-1), (nrows,))),
+                        device=E.device)
+    if out is None:
+        out = torch.empty((nrows, L), dtype=E.dtype, device=E.device)
+    assert out.shape == E.shape and out.stride(1) == 1 and out.dtype == E.dtype
+    _lib.check(_lib.load().qb_freq_shift_dev(_CODE[E.dtype], _ptr(E), nrows, E.stride(0), L, _ptr(f), int(os), int(t0),
+                                             _ptr(out), out.stride(0), _stream()))
+    return out
+
+
+def pilot_cpe(E, pilot_idx, pilots, num_average, want_trace=False):
+    """``pilot_based_cpe_new`` (pilotbased_receiver.py:258-327) for one frame per row of ``E`` (nrows, nlen):
+    ``pilot_idx`` (npilots) sorted positions, ``pilots`` (nrows, npilots) reference pilots.  Returns
+    (compensated rows, phase trace or None)."""
+    _check_cuda(E, pilots)
+    assert E.dim() == 2 and E.stride(1) == 1 and pilots.dim() == 2 and pilots.stride(1) == 1
+    nrows, nlen = E.shape
+    assert pilots.shape[0] == nrows and pilots.dtype == E.dtype
+    if not (num_average % 2):
+        num_average += 1
+    idx = torch.as_tensor(np.ascontiguousarray(pilot_idx, dtype=np.int64), device=E.device)
+    assert idx.numel() == pilots.shape[1] and int(idx[-1]) < nlen
+    out = torch.empty((nrows, nlen), dtype=E.dtype, device=E.device)
+    trace = torch.empty((nrows, nlen), dtype=_REAL[E.dtype], device=E.device) if want_trace else None
+    _lib.check(_lib.load().qb_pilot_cpe_dev(_CODE[E.dtype], _ptr(E), nrows, E.stride(0), nlen, _ptr(idx), _ptr(pilots),
+                                            pilots.stride(0), idx.numel(), int(num_average), _ptr(out), out.stride(0),
+                                            _ptr(trace), trace.stride(0) if want_trace else 0, _stream()))
+    return out, trace

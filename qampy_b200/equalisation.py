@@ -144,7 +144,7 @@ def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=
     ``apply``, the equalised windows ``(nwin, len(modes), (window - Ntaps + 1)//os)`` first -- NumPy arrays."""
     starts = np.atleast_1d(np.asarray(starts, dtype=np.int64))
     method_l = method.lower()
-    if method_l in REAL_VALUED or starts.size < 2 or np.unique(np.diff(starts)).size > 1:
+    if method_l in REAL_VALUED or (starts.size > 1 and np.unique(np.diff(starts)).size > 1):
         outs, taps, errs = [], [], []
         Eh = E.cpu().numpy() if torch.is_tensor(E) else np.asarray(E)
         for k, s0 in enumerate(starts):         # irregular windows / real-valued methods: plain loop
@@ -172,7 +172,7 @@ def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=
     nmodes, L = Ed.shape
     modes = np.arange(nmodes) if modes is None else np.atleast_1d(modes)
     assert np.max(modes) < nmodes, "largest mode number is larger than shape of signal"
-    nwin, step = starts.size, int(starts[1] - starts[0])
+    nwin, step = starts.size, (int(starts[1] - starts[0]) if starts.size > 1 else 0)
     assert starts[0] >= 0 and starts[-1] + window <= L, "window beyond the end of the signal"
     if wxy is None:
         w0 = theory.init_taps(Ntaps, nmodes, cdtype)
@@ -204,9 +204,10 @@ def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=
     return res
 
 
-def apply_windows(E, starts, window, os, wxy, modes=None):
+def apply_windows(E, starts, window, os, wxy, modes=None, as_tensor=False):
     """``apply_filter(E[:, s:s + window], os, wxy[k])`` for every window k as one launch (per-window taps
-    ``wxy`` (nwin, nmodes, nmodes, Ntaps), or one shared set).  Returns (nwin, len(modes), (window-Ntaps+1)//os)."""
+    ``wxy`` (nwin, nmodes, nmodes, Ntaps), or one shared set).  Returns (nwin, len(modes), (window-Ntaps+1)//os),
+    a NumPy array or (``as_tensor``) a CUDA tensor."""
     starts = np.atleast_1d(np.asarray(starts, dtype=np.int64))
     dev = _dev()
     if torch.is_tensor(E):
@@ -226,10 +227,12 @@ def apply_windows(E, starts, window, os, wxy, modes=None):
     if nwin > 1 and np.unique(np.diff(starts)).size == 1 and starts[1] > starts[0]:
         Ev = Ed.as_strided((nwin, nmodes, int(window)), (int(starts[1] - starts[0]), Ed.stride(0), 1),
                            Ed.storage_offset() + int(starts[0]))
-        return device.apply_filter_to_signal(Ev, int(os), wd, modes).cpu().numpy()
+        out = device.apply_filter_to_signal(Ev, int(os), wd, modes)
+        return out if as_tensor else out.cpu().numpy()
     outs = [device.apply_filter_to_signal(Ed[None, :, int(s0):int(s0) + int(window)], int(os), wd[k:k + 1], modes)[0]
             for k, s0 in enumerate(starts)]
-    return torch.stack(outs).cpu().numpy()
+    out = torch.stack(outs)
+    return out if as_tensor else out.cpu().numpy()
 
 
 def _equalise_signal_real(E, os, mu, M, wxy, Ntaps, TrSyms, Niter, method, adaptive_stepsize, symbols, modes,

@@ -171,7 +171,8 @@ def _train_windows(be, rx, starts, window, os, mu, M_pilot, Ntaps, eqargs):
     return np.asarray(taps), np.asarray(errs)
 
 
-def frame_sync(rx_signal, ref_symbs, os, frame_len=2 ** 16, M_pilot=4, mu=1e-3, Ntaps=17, backend=None, **eqargs):
+def frame_sync(rx_signal, ref_symbs, os, frame_len=2 ** 16, M_pilot=4, mu=1e-3, Ntaps=17, backend=None,
+               rx_device=None, **eqargs):
     """Locate the pilot sequence inside a frame (pilotbased_receiver.py:329-434).
 
     A blind equaliser (``eqargs``: method, Niter, adaptive_stepsize ...) is trained on windows of one
@@ -202,7 +203,9 @@ def frame_sync(rx_signal, ref_symbs, os, frame_len=2 ** 16, M_pilot=4, mu=1e-3, 
     num_steps = (frame_len * os) // step + 1      # one frame plus one extra step
     first = overlap                               # the first window position is skipped
     starts = np.arange(first, num_steps) * step
-    taps, errs = _train_windows(be, rx_signal, starts, window, os, mu, M_pilot, Ntaps, eqargs)
+    # rx_device: the same signal already on the GPU (saves the upload of the capture for the window training)
+    taps, errs = _train_windows(be, rx_signal if rx_device is None else rx_device, starts, window, os, mu, M_pilot,
+                                Ntaps, eqargs)
     sub_vars = np.ones((nmodes, num_steps)) * 1e2
     sub_vars[:, first:] = np.var(errs, axis=-1).T
     wxys = np.zeros((num_steps, nmodes, nmodes, Ntaps), dtype=rx_signal.dtype)
@@ -370,7 +373,7 @@ def pilot_equaliser(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, 
 
 
 def _pilot_frames_batched(be, rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps, frames, wxinit,
-                          apply, M_pilot=4, Niter=30, adaptive_stepsize=True, methods=('cma', 'cma')):
+                          apply, M_pilot=4, Niter=30, adaptive_stepsize=True, methods=('cma', 'cma'), as_tensor=False):
     """equalize_pilot_sequence + apply for several frames that start from the SAME initial taps, without
     frequency offset estimation: every training stage is one batched launch over the frames (one segment
     per frame, strided views of the capture).  Frame f gives what ``pilot_equaliser(frame=f)`` gives."""
@@ -411,11 +414,17 @@ def _pilot_frames_batched(be, rx_signal, pilot_seq, shiftfctrs, os, frame_len, m
         "Trying to equalise frame {}, but signal is not long enough".format(frames.max())
     if np.unique(ashifts).shape[0] > 1:
         mode_groups = np.arange(taps.shape[-3]).reshape(-1, npols).T
-        rows = [be.apply_windows(rx_signal, ashifts[mode[0]] + os * frame_len * frames, aspan, os, taps, modes=mode)
+        kw = {"as_tensor": True} if as_tensor else {}
+        rows = [be.apply_windows(rx_signal, ashifts[mode[0]] + os * frame_len * frames, aspan, os, taps, modes=mode, **kw)
                 for mode in mode_groups]
-        eq = np.concatenate(rows, axis=1)       # (nframes, nmodes, frame_len)
+        if as_tensor:
+            import torch
+            eq = torch.cat(rows, dim=1)
+        else:
+            eq = np.concatenate(rows, axis=1)   # (nframes, nmodes, frame_len)
     else:
-        eq = be.apply_windows(rx_signal, ashifts[0] + os * frame_len * frames, aspan, os, taps)
+        kw = {"as_tensor": True} if as_tensor else {}
+        eq = be.apply_windows(rx_signal, ashifts[0] + os * frame_len * frames, aspan, os, taps, **kw)
     return taps, eq
 
 
@@ -474,3 +483,70 @@ def pilot_equaliser_nframes(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu,
             foe_all.append(ret[1])
         k += 1
     return taps_all, (np.hstack(eq_all) if apply else None), foe_all
+
+
+def pilot_receiver(rx_signal, pilot_seq, ph_pilots, idx_pil, frame_len, os, frames, mu=(1e-3, 1e-3), Ntaps=45,
+                   num_average=5, M_pilot=4, methods=("cma", "sbd"), Niter=30, adaptive_stepsize=True,
+                   sync_kwargs=None, to_host=True):
+    """The pilot-based receiver chain of BASELINE config C4 with the capture resident on the GPU:
+
+        sync2frame -> corr_foe -> pilot_equaliser_nframes(foe_comp=False) -> pilot_cpe(use_seq=False) per frame
+
+    (``signals.py:1709-1747``, ``qampy/equalisation.py:336-397``, ``qampy/phaserec.py:156-192``).  One upload of
+    the capture; the frame search, the frequency shift, the pilot trainings of all frames (frame 0 first, the
+    others side by side from its taps), the FIRs and the per-frame phase recovery are CUDA launches on device
+    data; the host sees a 4k-sample stretch for the sequence correlation and the final result.
+
+    ``ph_pilots`` (nmodes, n_ph): the phase pilots of one frame; ``idx_pil`` (frame_len,) bool: pilot positions
+    in a frame (the first ``pilot_seq.shape[-1]`` are the sequence).  Returns a dict: ``out`` (nmodes,
+    nframes*frame_len) phase-compensated frames, ``eq`` the same before phase recovery, ``taps`` per frame,
+    ``shiftfctrs``, ``foe``, ``mode_order``, ``sync_ok``."""
+    import torch
+    from . import device, equalisation as be
+    from ._lib import require_device
+    require_device()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rx_host = None if torch.is_tensor(rx_signal) else np.atleast_2d(np.asarray(rx_signal))
+    Ed = rx_signal.to(dev) if torch.is_tensor(rx_signal) else torch.from_numpy(np.ascontiguousarray(rx_host)).to(dev)
+    if rx_host is None:
+        rx_host = Ed.cpu().numpy()
+    pilot_seq = np.atleast_2d(pilot_seq)
+    sl = pilot_seq.shape[-1]
+    # sync2frame (signals.py:1709-1741)
+    eqargs = {"adaptive_stepsize": True, "Niter": 10, "method": "cma", "Ntaps": 17, "mu": 5e-3}
+    eqargs.update(sync_kwargs or {})
+    mu_s, synctaps = eqargs.pop("mu"), eqargs.pop("Ntaps")
+    shift, foe, order, _, ok = frame_sync(rx_host, pilot_seq, os, frame_len=frame_len, M_pilot=M_pilot, mu=mu_s,
+                                          Ntaps=synctaps, rx_device=Ed, **eqargs)
+    shift[shift < 0] += frame_len * os
+    shiftf = shift[order]
+    Ed = Ed[torch.as_tensor(order, device=dev)].contiguous()
+    # corr_foe (signals.py:1744-1747)
+    foe = np.asarray(foe)
+    Ed = device.freq_shift(Ed, np.ones(foe.shape[0]) * np.mean(foe), os)
+    # pilot equaliser: frame 0 (or the first listed frame) from centre-spike taps, the rest from its taps, batched
+    frames = np.atleast_1d(np.asarray(frames, dtype=np.int64))
+    mu2 = np.atleast_1d(mu)
+    mu2 = np.repeat(mu2, 2) if len(mu2) == 1 else mu2
+    kw = dict(M_pilot=M_pilot, Niter=Niter, adaptive_stepsize=adaptive_stepsize, methods=methods, as_tensor=True)
+    t0, e0 = _pilot_frames_batched(be, Ed, pilot_seq, shiftf, os, frame_len, mu2, Ntaps, synctaps, frames[:1], None,
+                                   True, **kw)
+    taps, eqs = [t0[0]], [e0]
+    if len(frames) > 1:
+        t1, e1 = _pilot_frames_batched(be, Ed, pilot_seq, shiftf, os, frame_len, mu2, Ntaps, synctaps, frames[1:],
+                                       t0[0], True, **kw)
+        taps += [t1[j] for j in range(len(frames) - 1)]
+        eqs.append(e1)
+    eq = torch.cat(eqs, dim=0)                                   # (nframes, nmodes, frame_len)
+    nfr, nmodes = eq.shape[0], eq.shape[1]
+    # pilot_cpe(use_seq=False): phase pilots only (qampy/phaserec.py:183-186)
+    idx = np.nonzero(np.asarray(idx_pil))[0][sl:]
+    php = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(ph_pilots)[:, :idx.size])).to(dev).to(eq.dtype)
+    rows = eq.reshape(nfr * nmodes, frame_len)
+    out, _ = device.pilot_cpe(rows, idx, php.repeat(nfr, 1), num_average)
+    out = out.reshape(nfr, nmodes, frame_len).permute(1, 0, 2).reshape(nmodes, nfr * frame_len)
+    eq2 = eq.permute(1, 0, 2).reshape(nmodes, nfr * frame_len)
+    res = dict(out=out, eq=eq2, taps=taps, shiftfctrs=shiftf, foe=foe, mode_order=order, sync_ok=ok)
+    if to_host:
+        res["out"], res["eq"] = out.cpu().numpy(), eq2.cpu().numpy()
+    return res

@@ -26,6 +26,27 @@ for rep in range(2):
     dt, eq, outs = chain(be, frames)
 print('CUDA  frame_sync %.3f s  corr_foe %.3f s  pilot_eq(59 frames) %.3f s  cpe %.3f s  total %.3f s  -> %.1f Msymbols/s' %
       (*dt, dt.sum(), 2 * 59 * fl / dt.sum() / 1e6))
+alphabet = theory.normalised_symbols(M).astype(np.complex64)
+def ser_of(out, nfr_check=(0, 1, 57, 58)):
+    sy = d["symbols"].cpu().numpy(); e = []
+    for f in nfr_check:
+        data = out[:, f * fl:(f + 1) * fl][:, ~idx_pil]; ref = sy[:, f * fl:(f + 1) * fl][:, ~idx_pil]
+        dec = np.concatenate([alphabet[np.argmin(np.abs(data[:, a:a + 8192, None] - alphabet[None, None, :]), axis=-1)] for a in range(0, data.shape[1], 8192)], axis=1)
+        e.append(float(np.mean(np.abs(dec - ref) > 1e-3)))
+    return e
+print('SER (array chain) frames 0,1,57,58:', ser_of(np.hstack(outs)))
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = pilots.pilot_receiver(rx, seq, php[:, :idx.size], idx_pil, fl, 2, frames, to_host=True)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+print('CUDA device-resident chain (host capture in, host result out): %.3f s -> %.1f Msymbols/s' % (t1 - t0, 2 * 59 * fl / (t1 - t0) / 1e6))
+Ed = d["E"]
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res2 = pilots.pilot_receiver(Ed, seq, php[:, :idx.size], idx_pil, fl, 2, frames, to_host=False)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+print('CUDA device-resident chain (capture and result stay in HBM): %.3f s -> %.1f Msymbols/s' % (t1 - t0, 2 * 59 * fl / (t1 - t0) / 1e6))
+print('SER (device chain) frames 0,1,57,58:', ser_of(res["out"]))
 dt2, _, _ = chain(be, frames, batched=False)
 print('CUDA frame-by-frame pilot_eq %.3f s' % dt2[2])
 if '--cpu' in sys.argv:

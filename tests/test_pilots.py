@@ -211,3 +211,34 @@ def test_full_size_c4_pilot_receiver():
     t2, e2 = pilots.pilot_equaliser(rx3, seq, shiftf, 2, fl, (1e-3, 1e-3), 45, synctaps=17, foe_comp=False,
                                     wxinit=taps[0].copy(), frame=f, methods=("cma", "sbd"), backend=ORACLE)
     assert np.max(np.abs(t2 - taps[f])) < 1e-4 and rms(e2 - e1) < 1e-4
+
+
+@pytest.mark.gpu
+def test_device_resident_chain_matches_array_chain(golden):
+    """pilots.pilot_receiver (capture resident on the GPU: frequency shift and pilot phase recovery as CUDA
+    kernels) against the NumPy-glued chain on the reference's golden signal, and the two element-wise kernels
+    against NumPy directly."""
+    import torch
+    from qampy_b200 import device
+    g = golden("g9_pilot_rx")
+    be = _cuda_backend()
+    rx, seq, fl, osf = g["rx"], g["pilot_seq"], int(g["frame_len"]), int(g["os"])
+    sl = seq.shape[-1]
+    idx = np.nonzero(g["idx_pil"])[0][sl:]
+    php = g["ph_pilots"][:, :idx.size]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = pilots.pilot_receiver(rx, seq, php, g["idx_pil"], fl, osf, frames=[0, 1])
+    assert res["sync_ok"] and np.array_equal(res["shiftfctrs"], g["shiftfctrs"])
+    assert rms(res["eq"][:, :fl] - g["eq_frame0"]) < 1e-4
+    assert rms(res["out"][:, :fl] - g["cpe_out"]) < 1e-4
+    assert np.max(np.abs(res["taps"][0] - g["taps_sbd"])) < 1e-4
+    # kernels alone: frequency shift == comp_freq_offset, pilot CPE == pilot_based_cpe_new (NumPy, float64 ramp)
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(rx[:, :50000].copy()).to(dev)
+    foe = np.array([[1.2345e-3], [-2.5e-4]])
+    assert rms(device.freq_shift(x, foe, 2).cpu().numpy() - pilots.comp_freq_offset(rx[:, :50000], foe, 2)) < 2e-6
+    eq0 = torch.from_numpy(g["eq_frame0"].copy()).to(dev)
+    out, tr = device.pilot_cpe(eq0, idx, torch.from_numpy(php.copy()).to(dev), 5, want_trace=True)
+    assert rms(out.cpu().numpy() - g["cpe_out"]) < 2e-6
+    assert np.max(np.abs(tr.cpu().numpy() - g["cpe_trace"].real)) < 2e-6
