@@ -158,6 +158,23 @@ int qb_bps_rows_host(int dtype, const void *E, int64_t nstream, int64_t L, const
 int qb_detect_grid_host(int dtype, const void *symbols, int64_t M, void *lev_re, int64_t *n_re,
                         void *lev_im, int64_t *n_im);
 
+/* ---- decisions and quality metrics -----------------------------------------------------
+ * qb_make_decision_*: make_decision, qampy/core/equalisation/pythran_equalisation.py:306-334 -- for every
+ *     E[i]: idx = first minimum of |E[i] - symbols[j]| (np.argmin of np.abs, :232-235), det = symbols[idx],
+ *     dist = that modulus.  det / dist / idx may be NULL.
+ * qb_soft_l_value_demapper_host: soft_l_value_demapper (minmax = 0, pythran_dsp.py:95-108) and
+ *     soft_l_value_demapper_minmax (minmax = 1, :110-131); bits_map (nbits_map, K, 2) complex, L_values
+ *     (N, num_bits) float64 like the reference's output array.
+ * qb_estimate_snr_host: estimate_snr, pythran_dsp.py:244-286; out3 = (snr, signal power, noise power). */
+int qb_make_decision_dev(int dtype, const void *E, int64_t L, const void *symbols, int64_t M, void *det, void *dist,
+                         int32_t *idx, void *stream);
+int qb_make_decision_host(int dtype, const void *E, int64_t L, const void *symbols, int64_t M, void *det, void *dist,
+                          int32_t *idx);
+int qb_soft_l_value_demapper_host(int dtype, const void *rx, int64_t N, int64_t num_bits, double snr,
+                                  const void *bits_map, int64_t nbits_map, int64_t K, int minmax, double *L_values);
+int qb_estimate_snr_host(int dtype, const void *signal_rx, const void *symbols_tx, int64_t n,
+                         const void *gray_symbols, int64_t ngray, double *out3);
+
 /* ---- element-wise stages of the pilot-based receiver (device pointers only) ----------------------
  * qb_freq_shift_dev: comp_freq_offset, qampy/core/phaserecovery.py:438-473:
  *     out[r, t] = E[r, t] * exp(-2j*pi*(t0 + t + 1)*freq[r]/os),  freq (nrows) float64 on the device;

@@ -441,3 +441,52 @@ def equalise_signal_real(E, os_, mu, M, Ntaps, method, TrSyms=None, Niter=1, ada
     out = apply_filter_to_signal(Er.astype(ct), os_, wxy.astype(ct), modes).real
     Im = np.complex64(1j) if Er.itemsize == 4 else np.complex128(1j)
     return theory.convert_sig_to_cmplx(out, modes.shape[0], Im), wxy, err
+
+
+# --------------------------------------------------------------------------------------
+# decisions and quality metrics: NumPy restatements
+# --------------------------------------------------------------------------------------
+def make_decision(E, symbols):
+    """pythran_equalisation.py:306-334 with det_symbol_argmin (:232-235), vectorised in chunks."""
+    E = np.asarray(E)
+    symbols = np.asarray(symbols, dtype=E.dtype)
+    det = np.zeros_like(E)
+    dist = np.zeros(E.shape, dtype=E.real.dtype)
+    idx = np.zeros(E.shape, dtype=np.int32)
+    for a in range(0, E.shape[0], 16384):
+        d = np.abs(E[a:a + 16384, None] - symbols[None, :])
+        ix = np.argmin(d, axis=1)
+        idx[a:a + 16384] = ix
+        dist[a:a + 16384] = d[np.arange(ix.size), ix]
+        det[a:a + 16384] = symbols[ix]
+    return det, dist, idx
+
+
+def soft_l_value_demapper(rx_symbs, num_bits, snr, bits_map, minmax=False):
+    """pythran_dsp.py:95-108 (exact) and :110-131 (max-log), evaluated in the signal's precision."""
+    rx = np.asarray(rx_symbs)
+    rt = rx.real.dtype.type
+    out = np.zeros((rx.shape[0], num_bits))
+    for bit in range(num_bits):
+        d1 = np.abs(bits_map[bit, :, 1][None, :] - rx[:, None]) ** 2
+        d0 = np.abs(bits_map[bit, :, 0][None, :] - rx[:, None]) ** 2
+        if minmax:
+            out[:, bit] = rt(snr) * (np.minimum(d0.min(axis=1), rt(10000.)) - np.minimum(d1.min(axis=1), rt(10000.)))
+        else:
+            out[:, bit] = np.log(np.sum(np.exp(-rt(snr) * d1), axis=1)) - np.log(np.sum(np.exp(-rt(snr) * d0), axis=1))
+    return out
+
+
+def estimate_snr(signal_rx, symbols_tx, gray_symbols):
+    """pythran_dsp.py:244-286."""
+    L = signal_rx.shape[0]
+    in_pow, N0 = 0., 0.
+    for g in gray_symbols:
+        sel = signal_rx[symbols_tx == g]
+        K = sel.shape[0]
+        Px = K / L
+        mu = np.mean(sel)
+        sigma = np.sqrt(np.sum(abs(sel - mu) ** 2) / K)
+        N0 += abs(sigma) ** 2 * Px
+        in_pow += abs(mu) ** 2 * Px
+    return in_pow / N0, in_pow, N0

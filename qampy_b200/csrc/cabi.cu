@@ -46,6 +46,13 @@ int pilot_cpe_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stri
                        const void *pilots, int64_t pilot_stride, int64_t nph, int64_t navg, void *out,
                        int64_t out_stride, void *trace, int64_t trace_stride, cudaStream_t st);
 
+int make_decision_dispatch(int dtype, const void *E, int64_t L, const void *symbols, int64_t M, void *det, void *dist,
+                           int32_t *idx, cudaStream_t st);
+int demapper_dispatch(int dtype, const void *rx, int64_t N, int64_t num_bits, double snr, const void *bits_map, int64_t K,
+                      int minmax, double *Lv, cudaStream_t st);
+int snr_pass_dispatch(int dtype, const void *rx, const void *tx, int64_t n, const void *gray, int64_t Ncls,
+                      const double *means, double *acc, int pass, cudaStream_t st);
+
 static inline size_t csize(int dtype) { return dtype == QB_C64 ? 8 : 16; }
 static inline size_t rsize(int dtype) { return dtype == QB_C64 ? 4 : 8; }
 
@@ -424,6 +431,105 @@ static int bps_host_impl(int dtype, const void *E, int64_t nstream, int64_t L, c
     if (ph) QB_CUDA_CHECK(cudaMemcpyAsync(ph, dP.p, nE * rs, cudaMemcpyDeviceToHost, st));
     if (Eout) QB_CUDA_CHECK(cudaMemcpyAsync(Eout, dO.p, nE * cs, cudaMemcpyDeviceToHost, st));
     QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
+}
+
+int qb_make_decision_dev(int dtype, const void *E, int64_t L, const void *symbols, int64_t M, void *det, void *dist,
+                         int32_t *idx, void *stream)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(L >= 0 && M >= 1 && symbols && (E || L == 0), "invalid arguments");
+    return make_decision_dispatch(dtype, E, L, symbols, M, det, dist, idx, (cudaStream_t)stream);
+}
+
+int qb_make_decision_host(int dtype, const void *E, int64_t L, const void *symbols, int64_t M, void *det, void *dist,
+                          int32_t *idx)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(L >= 0 && M >= 1 && symbols && (E || L == 0), "invalid arguments");
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    if (L == 0) return QB_OK;
+    const size_t cs = csize(dtype), rs = rsize(dtype);
+    DevBuf dE(st), dS(st), dD(st), dR(st), dI(st);
+    QB_TRY(dE.alloc(L * cs));
+    QB_TRY(dS.alloc(M * cs));
+    if (det) QB_TRY(dD.alloc(L * cs));
+    if (dist) QB_TRY(dR.alloc(L * rs));
+    if (idx) QB_TRY(dI.alloc(L * sizeof(int32_t)));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dE.p, E, L * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dS.p, symbols, M * cs, cudaMemcpyHostToDevice, st));
+    QB_TRY(make_decision_dispatch(dtype, dE.p, L, dS.p, M, det ? dD.p : nullptr, dist ? dR.p : nullptr,
+                                  idx ? (int32_t *)dI.p : nullptr, st));
+    if (det) QB_CUDA_CHECK(cudaMemcpyAsync(det, dD.p, L * cs, cudaMemcpyDeviceToHost, st));
+    if (dist) QB_CUDA_CHECK(cudaMemcpyAsync(dist, dR.p, L * rs, cudaMemcpyDeviceToHost, st));
+    if (idx) QB_CUDA_CHECK(cudaMemcpyAsync(idx, dI.p, L * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
+}
+
+int qb_soft_l_value_demapper_host(int dtype, const void *rx, int64_t N, int64_t num_bits, double snr, const void *bits_map,
+                                  int64_t nbits_map, int64_t K, int minmax, double *L_values)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(N >= 0 && num_bits >= 0 && K >= 1 && bits_map && L_values, "invalid arguments");
+    QB_REQUIRE(nbits_map >= num_bits, "bits_map has fewer bits than num_bits");   // pythran_dsp.py:96, :124
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    if (N == 0 || num_bits == 0) return QB_OK;
+    const size_t cs = csize(dtype);
+    DevBuf dR(st), dB(st), dL(st);
+    QB_TRY(dR.alloc(N * cs));
+    QB_TRY(dB.alloc((size_t)num_bits * K * 2 * cs));
+    QB_TRY(dL.alloc((size_t)N * num_bits * sizeof(double)));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dR.p, rx, N * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dB.p, bits_map, (size_t)num_bits * K * 2 * cs, cudaMemcpyHostToDevice, st));
+    QB_TRY(demapper_dispatch(dtype, dR.p, N, num_bits, snr, dB.p, K, minmax, (double *)dL.p, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(L_values, dL.p, (size_t)N * num_bits * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
+}
+
+int qb_estimate_snr_host(int dtype, const void *signal_rx, const void *symbols_tx, int64_t n, const void *gray_symbols,
+                         int64_t ngray, double *out3)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(n >= 1 && ngray >= 1 && ngray <= 1024 && signal_rx && symbols_tx && gray_symbols && out3, "invalid arguments");
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    const size_t cs = csize(dtype);
+    DevBuf dR(st), dT(st), dG(st), dA(st), dM(st);
+    QB_TRY(dR.alloc(n * cs));
+    QB_TRY(dT.alloc(n * cs));
+    QB_TRY(dG.alloc(ngray * cs));
+    QB_TRY(dA.alloc((size_t)ngray * 4 * sizeof(double)));
+    QB_TRY(dM.alloc((size_t)ngray * 2 * sizeof(double)));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dR.p, signal_rx, n * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dT.p, symbols_tx, n * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dG.p, gray_symbols, ngray * cs, cudaMemcpyHostToDevice, st));
+    QB_CUDA_CHECK(cudaMemsetAsync(dA.p, 0, (size_t)ngray * 4 * sizeof(double), st));
+    double *acc1 = (double *)dA.p, *acc2 = acc1 + 3 * ngray;
+    QB_TRY(snr_pass_dispatch(dtype, dR.p, dT.p, n, dG.p, ngray, nullptr, acc1, 1, st));
+    std::vector<double> h1(3 * ngray), means(2 * ngray), h2(ngray);
+    QB_CUDA_CHECK(cudaMemcpyAsync(h1.data(), acc1, 3 * ngray * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int64_t c = 0; c < ngray; c++) {
+        means[2 * c] = h1[3 * c + 1] / h1[3 * c];          // 0/0 = NaN for an unused alphabet point, like np.mean([])
+        means[2 * c + 1] = h1[3 * c + 2] / h1[3 * c];
+    }
+    QB_CUDA_CHECK(cudaMemcpyAsync(dM.p, means.data(), 2 * ngray * sizeof(double), cudaMemcpyHostToDevice, st));
+    QB_TRY(snr_pass_dispatch(dtype, dR.p, dT.p, n, dG.p, ngray, (const double *)dM.p, acc2, 2, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(h2.data(), acc2, ngray * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    double in_pow = 0., N0 = 0.;
+    for (int64_t c = 0; c < ngray; c++) {                  // pythran_dsp.py:272-281
+        const double K = h1[3 * c], Px = K / (double)n;
+        N0 += (h2[c] / K) * Px;
+        in_pow += (means[2 * c] * means[2 * c] + means[2 * c + 1] * means[2 * c + 1]) * Px;
+    }
+    out3[0] = in_pow / N0;
+    out3[1] = in_pow;
+    out3[2] = N0;
     return QB_OK;
 }
 

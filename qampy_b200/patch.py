@@ -39,6 +39,18 @@ def patch(level="l2"):
         _set(ref_pe, "apply_filter_to_signal", q_pe.apply_filter_to_signal)
         _set(cph, "_bps_idx_pyt", q_dsp.bps)
         _set(cph, "select_angles", q_dsp.select_angles)
+        # decisions and quality metrics are from-imported by the modules that use them
+        # (qampy/core/signal_quality.py:26-29, qampy/signals.py:48-49)
+        for modname in ("qampy.core.signal_quality", "qampy.signals"):
+            try:
+                mod = importlib.import_module(modname)
+            except Exception:
+                continue
+            for name, fn in (("make_decision", q_pe.make_decision), ("estimate_snr", q_dsp.estimate_snr),
+                             ("soft_l_value_demapper", q_dsp.soft_l_value_demapper),
+                             ("soft_l_value_demapper_minmax", q_dsp.soft_l_value_demapper_minmax)):
+                if hasattr(mod, name):
+                    _set(mod, name, fn)
     elif level == "l2":
         ref = {n: getattr(ceq, n) for n in ("equalise_signal", "dual_mode_equalisation", "apply_filter")}
 

@@ -54,3 +54,41 @@ def select_angles(angles, idx):
     out = np.zeros(L, dtype=rt)
     _lib.check(_lib.load().qb_select_angles_host(code, _p(angles), p, A, _p(idx), L, _p(out)))
     return out
+
+
+def _demap(rx_symbs, num_bits, snr, bits_map, minmax):
+    code, rt, ct = _ctype(np.asarray(rx_symbs).dtype)
+    rx = np.ascontiguousarray(rx_symbs, dtype=ct)
+    if rx.ndim != 1:
+        raise ValueError("rx_symbs must be 1-dimensional")
+    bm = np.ascontiguousarray(bits_map, dtype=ct)
+    assert bm.ndim == 3 and bm.shape[2] == 2 and bm.shape[0] >= num_bits
+    out = np.zeros((rx.shape[0], int(num_bits)))
+    _lib.check(_lib.load().qb_soft_l_value_demapper_host(code, _p(rx), rx.shape[0], int(num_bits), float(snr), _p(bm),
+                                                         bm.shape[0], bm.shape[1], int(minmax), _p(out)))
+    return out
+
+
+def soft_l_value_demapper(rx_symbs, num_bits, snr, bits_map):
+    """Exact log-likelihood ratios per bit (:95-108): ``bits_map[bit, :, b]`` are the alphabet points whose
+    ``bit`` equals ``b``.  Returns float64 (N, num_bits) like the reference."""
+    return _demap(rx_symbs, num_bits, snr, bits_map, False)
+
+
+def soft_l_value_demapper_minmax(rx_symbs, num_bits, snr, bits_map):
+    """Max-log approximation of the log-likelihood ratios (:110-131)."""
+    return _demap(rx_symbs, num_bits, snr, bits_map, True)
+
+
+def estimate_snr(signal_rx, symbols_tx, gray_symbols):
+    """SNR from received and known transmitted symbols (:244-286).  Returns ``(snr, S0, N0)`` (linear)."""
+    code, rt, ct = _ctype(np.asarray(signal_rx).dtype)
+    rx = np.ascontiguousarray(signal_rx, dtype=ct)
+    tx = np.ascontiguousarray(symbols_tx, dtype=ct)
+    assert rx.shape[0] >= tx.shape[0]
+    if rx.shape != tx.shape:
+        raise ValueError("signal_rx and symbols_tx need to have the same length")
+    gray = np.ascontiguousarray(gray_symbols, dtype=ct).reshape(-1)
+    out = np.zeros(3)
+    _lib.check(_lib.load().qb_estimate_snr_host(code, _p(rx), _p(tx), rx.shape[0], _p(gray), gray.size, _p(out)))
+    return out[0], out[1], out[2]

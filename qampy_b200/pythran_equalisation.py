@@ -145,3 +145,19 @@ def train_equaliser_realvalued(E, TrSyms, Niter, os, mu, wx, modes, adaptive, sy
         np.copyto(wx, wx_r)            # in-place contract (:107)
         wx_r = wx
     return np.ascontiguousarray(err.real), wx_r, mu_io[0]
+
+
+def make_decision(E, symbols):
+    """Decision operator (:306-334): for every sample the nearest alphabet point.  Returns
+    ``(det_symbs, dist, idx)`` -- decided symbols, their distance ``np.abs(E - s)`` and the int32 index."""
+    code, rt, ct = _ctype(np.asarray(E).dtype)
+    E = np.ascontiguousarray(E, dtype=ct)
+    if E.ndim != 1:
+        raise ValueError("E must be 1-dimensional")
+    symbols = np.ascontiguousarray(symbols, dtype=ct).reshape(-1)
+    det = np.zeros_like(E)
+    dist = np.zeros(E.shape, dtype=rt)
+    idx = np.zeros(E.shape, dtype=np.int32)
+    _lib.check(_lib.load().qb_make_decision_host(code, _p(E), E.shape[0], _p(symbols), symbols.size, _p(det), _p(dist),
+                                                 _p(idx)))
+    return det, dist, idx

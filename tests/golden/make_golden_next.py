@@ -13,6 +13,8 @@ G9  pilot-based receiver on arrays (qampy/core/pilotbased_receiver.py: frame_syn
     comp_freq_offset :385-473), the recipe of test/test_equalisation.py:150-164 at reduced size:
     dual-pol 16-QAM, frame 2**13, pilot sequence 512, one phase pilot per 32, 3 frames, SNR 25 dB,
     DGD 10 ps, 100 MHz offset, 100 kHz linewidth, modal delay 700 samples.
+G10 decisions and quality metrics: make_decision (pythran_equalisation.py:306-334), soft_l_value_demapper and
+    soft_l_value_demapper_minmax (pythran_dsp.py:95-131), estimate_snr (:244-286) on noisy 16/64-QAM, c64 and c128.
 """
 import os
 import sys
@@ -79,7 +81,8 @@ def main():
     from qampy.core.equalisation import equalisation as ceq2
     np.random.seed(91)
     fl, sl, rat, osf = 2 ** 13, 512, 32, 2
-    sig = signals.SignalWithPilots(16, fl, sl, rat, nframes=3, nmodes=2, Mpilots=4, fb=24e9, dtype=np.complex64)
+    sig = signals.SignalWithPilots(16, fl, sl, rat, nframes=3, nmodes=2, Mpilots=4, fb=24e9, dtype=np.complex64,
+                                   seed=[91, 92])      # bit sources seeded: the file regenerates identically
     s2 = sig.resample(2 * sig.fb, beta=0.01)
     s3 = impairments.simulate_transmission(s2, snr=25, dgd=10e-12, freq_off=100e6, lwdth=100e3,
                                            modal_delay=[700, 700])
@@ -116,6 +119,24 @@ def main():
     foe_p, foe_pm, cond = pr.pilot_based_foe(np.asarray(eq)[:, :sl], pilot_seq)
     out.update(pfoe=foe_p, pfoe_mode=foe_pm, pfoe_cond=cond)
     np.savez_compressed(os.path.join(HERE, "g9_pilot_rx.npz"), **out)
+    # ---- G10: decisions and metrics ---------------------------------------------------------------------------
+    from qampy.core.equalisation import pythran_equalisation as pe2
+    out = {}
+    for tag, dt, M, n, snr_db, seed in (("c64", np.complex64, 64, 3000, 11, 101), ("c128", np.complex128, 16, 2000, 12, 102)):
+        sg = signals.SignalQAMGrayCoded(M, n, nmodes=1, fb=40e9, dtype=dt, seed=[seed])
+        np.random.seed(seed)
+        rx = np.asarray(impairments.change_snr(sg, snr_db))[0]
+        coded = np.asarray(sg.coded_symbols)
+        det, dist, idx = pe2.make_decision(rx, coded)
+        bm = np.asarray(sg._bitmap_mtx)
+        snr_lin = dt(0).real.dtype.type(10 ** (snr_db / 10))
+        lv = pd.soft_l_value_demapper(rx, sg.Nbits, snr_lin, bm)
+        lvm = pd.soft_l_value_demapper_minmax(rx, sg.Nbits, snr_lin, bm)
+        est = pd.estimate_snr(rx, np.asarray(sg)[0], coded)
+        out.update({"rx_" + tag: rx, "tx_" + tag: np.asarray(sg)[0], "coded_" + tag: coded, "det_" + tag: det,
+                    "dist_" + tag: dist, "idx_" + tag: idx, "bitmap_" + tag: bm, "nbits_" + tag: sg.Nbits,
+                    "snr_" + tag: snr_lin, "lv_" + tag: lv, "lvmm_" + tag: lvm, "est_" + tag: np.array(est, dtype=np.float64)})
+    np.savez_compressed(os.path.join(HERE, "g10_decisions.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))

@@ -180,3 +180,23 @@ def test_real_valued_methods(golden, qb, tag, tol, method, adaptive):
     out = qb.pe.apply_filter_to_signal(Er, 2, g["wxy_" + key], np.arange(4))
     assert out.dtype == Er.dtype
     assert rms((out[:2] + 1j * out[2:]) - g["out_" + key]) < tol
+
+
+@pytest.mark.parametrize("tag", ["c64", "c128"])
+def test_decisions_and_metrics(golden, qb, tag):
+    """make_decision (indices exact), soft demappers and estimate_snr on the GPU against the reference's outputs."""
+    g = golden("g10_decisions")
+    rx, coded = g["rx_" + tag], g["coded_" + tag]
+    det, dist, idx = qb.pe.make_decision(rx, coded)
+    assert idx.dtype == np.int32 and det.dtype == rx.dtype and dist.dtype == rx.real.dtype
+    assert np.array_equal(idx, g["idx_" + tag]) and np.array_equal(det, g["det_" + tag])
+    assert np.allclose(dist, g["dist_" + tag], rtol=2e-7 if tag == "c64" else 1e-15, atol=0)
+    nb, snr, bm = int(g["nbits_" + tag]), g["snr_" + tag], g["bitmap_" + tag]
+    tol = 2e-4 if tag == "c64" else 1e-9
+    lv = qb.dsp.soft_l_value_demapper(rx, nb, snr, bm)
+    lvm = qb.dsp.soft_l_value_demapper_minmax(rx, nb, snr, bm)
+    assert lv.dtype == np.float64 and lv.shape == g["lv_" + tag].shape
+    assert np.max(np.abs(lv - g["lv_" + tag])) < tol * max(1.0, np.max(np.abs(g["lv_" + tag])))
+    assert np.max(np.abs(lvm - g["lvmm_" + tag])) < tol * max(1.0, np.max(np.abs(g["lvmm_" + tag])))
+    est = qb.dsp.estimate_snr(rx, g["tx_" + tag], coded)
+    assert np.allclose(est, g["est_" + tag], rtol=1e-5 if tag == "c64" else 1e-12)

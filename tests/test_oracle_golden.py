@@ -170,3 +170,18 @@ def test_real_valued_methods(golden, tag, tol, method, adaptive):
     assert np.max(np.abs(wxy - g["wxy_" + key])) < tol
     if method != "sgncma_real":                       # sign() of a value at rounding distance from 0 may flip
         assert rms(err - g["err_" + key]) < tol
+
+
+@pytest.mark.parametrize("tag", ["c64", "c128"])
+def test_decisions_and_metrics(golden, tag):
+    """make_decision, the soft demappers and estimate_snr: NumPy restatements vs the reference."""
+    g = golden("g10_decisions")
+    rx, coded = g["rx_" + tag], g["coded_" + tag]
+    det, dist, idx = co.make_decision(rx, coded)
+    assert np.array_equal(idx, g["idx_" + tag]) and np.array_equal(det, g["det_" + tag])
+    assert np.allclose(dist, g["dist_" + tag], rtol=1e-6, atol=0)
+    nb, snr, bm = int(g["nbits_" + tag]), g["snr_" + tag], g["bitmap_" + tag]
+    tol = 2e-4 if tag == "c64" else 1e-9
+    assert np.max(np.abs(co.soft_l_value_demapper(rx, nb, snr, bm) - g["lv_" + tag])) < tol * max(1.0, np.max(np.abs(g["lv_" + tag])))
+    assert np.max(np.abs(co.soft_l_value_demapper(rx, nb, snr, bm, minmax=True) - g["lvmm_" + tag])) < tol * max(1.0, np.max(np.abs(g["lvmm_" + tag])))
+    assert np.allclose(co.estimate_snr(rx, g["tx_" + tag], coded), g["est_" + tag], rtol=1e-5 if tag == "c64" else 1e-12)
