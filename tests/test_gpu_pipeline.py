@@ -217,3 +217,32 @@ def test_full_size_c3_properties(env):
     rhs = 0.5 * f(E) + f(E2)
     assert float((lhs - rhs).abs().max()) < 2e-5
     assert lhs.shape[1] == (E.shape[1] - ntaps + 1) // 2
+
+
+def test_full_size_c2_properties(env):
+    """BASELINE config C2 at full size: dual-pol 16-QAM, MCMA ntaps 21, 1e6 symbols, BPS(32 angles, N = 21), as
+    time segments: a segment out of the batch is bit-identical to that segment alone and matches the oracle."""
+    t = env.torch
+    M, ntaps, S, A, N = 16, 21, 4096, 32, 21
+    E, syms = env.synth.synth_signal(M, 10 ** 6, seed=21, snr_db=25.0, theta=np.pi / 5, dgd=30e-12, device=env.dev)
+    cfg = env.pipeline.ReceiverConfig(M=M, ntaps=ntaps, mu=(1e-3,), methods=("mcma",), niter=(1,), bps_angles=A, bps_N=N,
+                                      seg_symbols=S)
+    rx = env.pipeline.SegmentedReceiver(cfg, env.dev)
+    g = rx.run(E)[0]
+    assert g["nseg"] == (10 ** 6 * 2 - ntaps + 1) // 2 // S
+    assert t.isfinite(t.view_as_real(g["out"])).all()
+    one = env.pipeline.SegmentedReceiver(env.pipeline.ReceiverConfig(M=M, ntaps=ntaps, mu=(1e-3,), methods=("mcma",),
+                                                                     niter=(1,), bps_angles=A, bps_N=N), env.dev)
+    alphabet = env.theory.normalised_symbols(M).astype(np.complex64)
+    for s in (0, 131, g["nseg"] - 1):
+        seg = E[:, s * S * 2: s * S * 2 + S * 2 + ntaps - 1].contiguous()
+        alone = one.run(seg)[0]
+        for key in ("eq", "out", "ph", "idx", "taps"):
+            assert t.equal(alone[key][0], g[key][s]), (key, s)
+    s = 77
+    seg = E[:, s * S * 2: s * S * 2 + S * 2 + ntaps - 1].cpu().numpy()
+    Er, wr, _ = env.co.equalise_signal(seg, 2, 1e-3, M, Ntaps=ntaps, method="mcma", apply=True)
+    assert rms(g["eq"][s].cpu().numpy() - Er) < 1e-5 and np.max(np.abs(g["taps"][s].cpu().numpy() - wr)) < 1e-5
+    Eb, phr = env.co.bps_driver(g["eq"][s].cpu().numpy(), A, alphabet, N)
+    assert np.array_equal(g["ph"][s].cpu().numpy(), phr) and rms(g["out"][s].cpu().numpy() - Eb) < 1e-6
+    assert 0.85 < rms(g["eq"].cpu().numpy()) < 1.15          # not a collapsed equaliser
