@@ -69,7 +69,7 @@ def workload_config(a, world):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  The region lasts tens of milliseconds, so
-    the sampler polls NVML in a thread (about 1 kHz) instead of `nvidia-smi -lms`, whose first line arrives
+    the sampler polls NVML in a thread (every 2 ms) instead of `nvidia-smi -lms`, whose first line arrives
     after the region has ended; nvidia-smi is the fallback when pynvml is missing."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                ("sw_power_cap", 0x4))
@@ -91,6 +91,11 @@ class ClockSampler:
                 if index < len(ids) and ids[index].isdigit():
                     phys = int(ids[index])
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            # the first queries of a process take tens of milliseconds inside the driver and can hold up kernel
+            # launches (scratch/step_probe.py): pay for them here, before the timed region starts
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
             self.nvml = pynvml
         except Exception:
             self.nvml = None
@@ -104,7 +109,7 @@ class ClockSampler:
                 self.samples.append((float(sm), int(mask)))
             except Exception:
                 break
-            time.sleep(0.0005)
+            time.sleep(0.002)
 
     def start(self):
         if self.nvml is not None:

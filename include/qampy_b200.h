@@ -190,6 +190,15 @@ int qb_pilot_cpe_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride
                      int64_t num_average, void *out, int64_t out_stride, void *trace, int64_t trace_stride,
                      void *stream);
 
+/* ---- Viterbi-Viterbi M-th power phase recovery, qampy/core/phaserecovery.py:40-79 ---------------------
+ * For every row r of E (nrows, L): ph[r, w] = (unwrap(angle(sum_{t=w..w+N-1} (E[r,t]/|E[r,t]|)^M)) - pi)/M for the
+ * L-N+1 windows, out[r, o+w] = E[r, o+w]*exp(-1j*ph[r, w]) with o = (N-1)/2 and zeros where no full window
+ * exists.  ph rows are ph_stride (dev) / L-N+1 (host) real elements apart.  1 <= N <= 512.             */
+int qb_viterbiviterbi_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, int64_t N, int64_t M,
+                          void *out, int64_t out_stride, void *ph, int64_t ph_stride, void *stream);
+int qb_viterbiviterbi_host(int dtype, const void *E, int64_t nrows, int64_t L, int64_t N, int64_t M, void *out,
+                           void *ph);
+
 /* ---- select_angles(angles, idx): out[i] = angles[p > 1 ? i : 0][idx[i]] ----------------------- */
 int qb_select_angles_dev(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
                          int64_t L, void *out, void *stream);

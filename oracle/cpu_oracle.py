@@ -490,3 +490,20 @@ def estimate_snr(signal_rx, symbols_tx, gray_symbols):
         N0 += abs(sigma) ** 2 * Px
         in_pow += abs(mu) ** 2 * Px
     return in_pow / N0, in_pow, N0
+
+
+def viterbiviterbi(E, N, M):
+    """qampy/core/phaserecovery.py:40-79 restated in NumPy, every step in the dtype the reference uses (phase and
+    phasors in the signal's precision, window sum over a strided view).  Returns (Eout, phases of every row)."""
+    E2d = np.atleast_2d(np.asarray(E))
+    Eout = np.zeros_like(E2d)
+    L = E2d.shape[1]
+    o = (N - 1) // 2
+    phases = []
+    for i in range(E2d.shape[0]):
+        raised = np.exp(1.j * np.angle(E2d[i])) ** M                                   # :63-64
+        win = np.lib.stride_tricks.sliding_window_view(raised, N)                     # segment_axis(., N, N-1), :65
+        est = (np.unwrap(np.angle(np.sum(win, axis=1))) - np.pi) / M                  # :66-68
+        Eout[i, o:o + L - N + 1] = E2d[i, o:o + L - N + 1] * np.exp(-1.j * est)      # :69-72
+        phases.append(est)
+    return Eout, np.asarray(phases)

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "qb_make_decision_host": ([_int, _vp, _i64, _vp, _i64, _vp, _vp, _vp], _int),
     "qb_soft_l_value_demapper_host": ([_int, _vp, _i64, _i64, ctypes.c_double, _vp, _i64, _i64, _int, _vp], _int),
     "qb_estimate_snr_host": ([_int, _vp, _vp, _i64, _vp, _i64, _vp], _int),
+    "qb_viterbiviterbi_dev": ([_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp], _int),
+    "qb_viterbiviterbi_host": ([_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp], _int),
     "qb_freq_shift_dev": ([_int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp], _int),
     "qb_pilot_cpe_dev": ([_int, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp], _int),
     "qb_select_angles_dev": ([_int, _vp, _i64, _i64, _vp, _i64, _vp, _vp], _int),

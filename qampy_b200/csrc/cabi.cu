@@ -46,6 +46,10 @@ int pilot_cpe_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stri
                        const void *pilots, int64_t pilot_stride, int64_t nph, int64_t navg, void *out,
                        int64_t out_stride, void *trace, int64_t trace_stride, cudaStream_t st);
 
+int vv_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, int64_t N, int64_t M, void *out,
+                int64_t out_stride, void *ph, int64_t ph_stride, void *work, cudaStream_t st);
+size_t vv_work_bytes(int dtype, int64_t nrows, int64_t L, int64_t N);
+
 int make_decision_dispatch(int dtype, const void *E, int64_t L, const void *symbols, int64_t M, void *det, void *dist,
                            int32_t *idx, cudaStream_t st);
 int demapper_dispatch(int dtype, const void *rx, int64_t N, int64_t num_bits, double snr, const void *bits_map, int64_t K,
@@ -554,6 +558,50 @@ int qb_pilot_cpe_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride
     QB_REQUIRE(nrows == 0 || nlen == 0 || (E && pilot_idx && pilots && out), "E, pilot_idx, pilots and out must not be NULL");
     return pilot_cpe_dispatch(dtype, E, nrows, row_stride, nlen, pilot_idx, pilots, pilot_stride, npilots, num_average,
                               out, out_stride, trace, trace_stride, (cudaStream_t)stream);
+}
+
+static int vv_check(int64_t nrows, int64_t L, int64_t N, int64_t M)
+{
+    QB_REQUIRE(nrows >= 0 && nrows <= 65535, "between 0 and 65535 rows");
+    QB_REQUIRE(N >= 1 && L >= N, "the averaging length N must be between 1 and the signal length");
+    QB_REQUIRE(M >= 1 && M <= 1024, "PSK order M out of range");
+    return QB_OK;
+}
+
+int qb_viterbiviterbi_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, int64_t N, int64_t M,
+                          void *out, int64_t out_stride, void *ph, int64_t ph_stride, void *stream)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_TRY(vv_check(nrows, L, N, M));
+    QB_REQUIRE(nrows == 0 || (E && out && ph), "E, out and ph must not be NULL");
+    if (nrows == 0) return QB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf work(st);                                        // per-tile turn counts; stream-ordered, freed after the kernels
+    QB_TRY(work.alloc(vv_work_bytes(dtype, nrows, L, N)));
+    return vv_dispatch(dtype, E, nrows, row_stride, L, N, M, out, out_stride, ph, ph_stride, work.p, st);
+}
+
+int qb_viterbiviterbi_host(int dtype, const void *E, int64_t nrows, int64_t L, int64_t N, int64_t M, void *out, void *ph)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_TRY(vv_check(nrows, L, N, M));
+    QB_REQUIRE(nrows == 0 || (E && out && ph), "E, out and ph must not be NULL");
+    cudaStream_t st;
+    QB_TRY(host_stream(&st));
+    if (nrows == 0) return QB_OK;
+    const size_t cs = csize(dtype), rs = rsize(dtype);
+    const int64_t nwin = L - N + 1;
+    DevBuf dE(st), dO(st), dP(st), work(st);
+    QB_TRY(dE.alloc((size_t)nrows * L * cs));
+    QB_TRY(dO.alloc((size_t)nrows * L * cs));
+    QB_TRY(dP.alloc((size_t)nrows * nwin * rs));
+    QB_TRY(work.alloc(vv_work_bytes(dtype, nrows, L, N)));
+    QB_CUDA_CHECK(cudaMemcpyAsync(dE.p, E, (size_t)nrows * L * cs, cudaMemcpyHostToDevice, st));
+    QB_TRY(vv_dispatch(dtype, dE.p, nrows, L, L, N, M, dO.p, L, dP.p, nwin, work.p, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(out, dO.p, (size_t)nrows * L * cs, cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaMemcpyAsync(ph, dP.p, (size_t)nrows * nwin * rs, cudaMemcpyDeviceToHost, st));
+    QB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return QB_OK;
 }
 
 int qb_select_angles_dev(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx, int64_t L,

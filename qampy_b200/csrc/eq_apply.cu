@@ -192,27 +192,28 @@ __global__ void __launch_bounds__(A22_THREADS) apply_2x2_os2_kernel(Apply22Param
 #pragma unroll
     for (int r = 0; r < A22_R; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
     const int base = tid * A22_R;
+    // warps whose outputs all lie past the end of a ragged last tile skip the arithmetic (warp-uniform)
+    const int kend = (base - (tid & 31) * A22_R) < nout ? 2 : 0;
 #pragma unroll 1
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kend; k++) {
         const float4 *xr = xs + (size_t)k * npair_x + base;
         const float4 *w0 = ws + (0 * 2 + k) * npair_w;
         const float4 *w1 = ws + (1 * 2 + k) * npair_w;
+        // circular register window: at tap pair u, win[(r + u) % R] holds sample pair base + r + u.  u0 advances
+        // by R and uu is a compile-time index, so the rotation is pure register renaming (no moves).
         float4 win[A22_R];
 #pragma unroll
-        for (int r = 0; r < A22_R - 1; r++) win[r + 1] = xr[r];  // pre-load pairs base .. base+R-2
+        for (int r = 0; r < A22_R - 1; r++) win[r] = xr[r];  // pairs base .. base+R-2
         for (int u0 = 0; u0 < npair_w; u0 += A22_R) {
-            // unrolled by R so the register window rotates by renaming, not by moves
 #pragma unroll
             for (int uu = 0; uu < A22_R; uu++) {
                 const int u = u0 + uu;
                 if (u < npair_w) {
-#pragma unroll
-                    for (int r = 0; r < A22_R - 1; r++) win[r] = win[r + 1];
-                    win[A22_R - 1] = xr[u + A22_R - 1];
+                    win[(uu + A22_R - 1) % A22_R] = xr[u + A22_R - 1];   // replaces pair base + u - 1
                     const float4 a = w0[u], b = w1[u];
 #pragma unroll
                     for (int r = 0; r < A22_R; r++) {
-                        const float4 x = win[r];  // (x[2q].re, x[2q].im, x[2q+1].re, x[2q+1].im)
+                        const float4 x = win[(r + uu) % A22_R];  // (x[2q].re, x[2q].im, x[2q+1].re, x[2q+1].im)
                         acc[r][0] = fmaf(x.x, a.x, acc[r][0]);
                         acc[r][0] = fmaf(-x.y, a.y, acc[r][0]);
                         acc[r][1] = fmaf(x.x, a.y, acc[r][1]);

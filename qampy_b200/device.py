@@ -164,3 +164,16 @@ def pilot_cpe(E, pilot_idx, pilots, num_average, want_trace=False):
                                             pilots.stride(0), idx.numel(), int(num_average), _ptr(out), out.stride(0),
                                             _ptr(trace), trace.stride(0) if want_trace else 0, _stream()))
     return out, trace
+
+
+def viterbiviterbi(E, N, M):
+    """``viterbiviterbi`` (phaserecovery.py:40-79) for every row of ``E`` (nrows, L): returns (compensated rows
+    with zeros where no full window exists, phase estimates (nrows, L - N + 1))."""
+    _check_cuda(E)
+    assert E.dim() == 2 and E.stride(1) == 1
+    nrows, L = E.shape
+    out = torch.empty((nrows, L), dtype=E.dtype, device=E.device)
+    ph = torch.empty((nrows, max(L - int(N) + 1, 0)), dtype=_REAL[E.dtype], device=E.device)
+    _lib.check(_lib.load().qb_viterbiviterbi_dev(_CODE[E.dtype], _ptr(E), nrows, E.stride(0), L, int(N), int(M),
+                                                 _ptr(out), out.stride(0), _ptr(ph), ph.stride(0), _stream()))
+    return out, ph

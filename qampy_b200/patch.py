@@ -89,6 +89,7 @@ def patch(level="l2"):
             return q_ph.bps_twostage(E, Mtestangles, symbols, N, B=B, method=method, **kwargs)
 
         _set(cph, "bps_twostage", bps_twostage)
+        _set(cph, "viterbiviterbi", q_ph.viterbiviterbi)
     else:
         raise ValueError("level must be 'l1' or 'l2'")
     return [name for _, name, _ in _saved]

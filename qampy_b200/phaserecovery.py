@@ -61,3 +61,25 @@ def bps_twostage(E, Mtestangles, symbols, N, B=4, method="pyt", **kwargs):
     if E.ndim == 1:
         return En.flatten(), ph_out.flatten()
     return En, ph_out
+
+
+def viterbiviterbi(E, N, M):
+    """Viterbi-Viterbi blind phase recovery for an M-PSK signal, drop-in for
+    ``qampy/core/phaserecovery.py::viterbiviterbi`` (:40-79): M-th power, sliding sum over ``N`` symbols, unwrapped
+    angle, rotation; three CUDA kernels for all modes (``csrc/vv.cu``).  Returns ``(Eout, phase_est)`` like the
+    reference, including its quirk that for a 2-D input ``phase_est`` is the 1-D estimate of the LAST mode only
+    (:77-79); ``qampy_b200.device.viterbiviterbi`` returns the estimates of every row."""
+    Ein = E
+    E = np.asarray(E)
+    if E.dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+        raise TypeError("qampy_b200 viterbiviterbi needs a complex64/complex128 signal, got %s" % E.dtype)
+    _lib.require_device()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Ew = np.atleast_2d(E)
+    out, ph = device.viterbiviterbi(torch.from_numpy(np.ascontiguousarray(Ew)).to(dev), int(N), int(M))
+    Eout = np.zeros_like(np.atleast_2d(Ein), dtype=E.dtype)           # keeps the SignalObject subclass (:60)
+    Eout[...] = out.cpu().numpy()
+    phase_est = ph[-1].cpu().numpy()
+    if E.ndim == 1:
+        return Eout.flatten(), phase_est.flatten()
+    return Eout, phase_est

@@ -200,3 +200,42 @@ def test_decisions_and_metrics(golden, qb, tag):
     assert np.max(np.abs(lvm - g["lvmm_" + tag])) < tol * max(1.0, np.max(np.abs(g["lvmm_" + tag])))
     est = qb.dsp.estimate_snr(rx, g["tx_" + tag], coded)
     assert np.allclose(est, g["est_" + tag], rtol=1e-5 if tag == "c64" else 1e-12)
+
+
+def test_viterbiviterbi(golden, qb):
+    """Viterbi-Viterbi M-th power phase recovery (phaserecovery.py:40-79) through the drop-in API and the C ABI's
+    host entry point, against what the reference produced.  Floating-point tolerance: the reference rounds the
+    symbol phases, the phasors and their sums to the signal precision (|error| of the estimate ~ 1e-7 rad in
+    c64); the kernels accumulate in double and round the results."""
+    import cpu_oracle as co
+    from qampy_b200 import _lib
+    g = golden("g11_viterbi")
+    E = g["in_c64"]
+    for N in (10, 11):
+        Eo, ph = qb.ph.viterbiviterbi(E, N, 4)
+        assert Eo.dtype == np.complex64 and ph.dtype == np.float32 and ph.shape == g["ph_c64_%d" % N].shape
+        assert np.max(np.abs(ph - g["ph_c64_%d" % N])) < 2e-6                 # last mode only, like the reference
+        assert rms(Eo - g["out_c64_%d" % N]) < 2e-6
+        o = (N - 1) // 2
+        assert not Eo[:, :o].any() and not Eo[:, o + ph.size:].any()
+    E8 = g["in_c128"]
+    Eo, ph = qb.ph.viterbiviterbi(E8.reshape(1, -1), 7, 8)
+    assert ph.dtype == np.float64 and np.max(np.abs(ph - g["ph_c128"])) < 1e-12 and rms(Eo - g["out_c128"]) < 1e-12
+    Eo1, ph1 = qb.ph.viterbiviterbi(E8, 7, 8)                                  # 1-D in, 1-D out (:75-76)
+    assert Eo1.shape == E8.shape and ph1.ndim == 1 and rms(Eo1 - g["out1d_c128"]) < 1e-12
+    # C ABI host entry point, all rows' phases; several tiles and a ragged last tile against the oracle
+    rng = np.random.default_rng(5)
+    n = 3 * 2048 + 77
+    walk = np.cumsum(rng.normal(0, 0.03, (3, n)), axis=1)
+    Er = (np.exp(1j * (np.pi / 4 + np.pi / 2 * rng.integers(0, 4, (3, n)) + walk))
+          + 0.05 * (rng.normal(size=(3, n)) + 1j * rng.normal(size=(3, n)))).astype(np.complex64)
+    for N in (1, 2, 33):
+        out = np.empty_like(Er)
+        ph = np.empty((3, n - N + 1), np.float32)
+        _lib.check(_lib.load().qb_viterbiviterbi_host(0, Er.ctypes.data, 3, n, N, 4, out.ctypes.data, ph.ctypes.data))
+        Eo, pho = co.viterbiviterbi(Er, N, 4)
+        assert np.max(np.abs(ph - pho)) < 1e-5 and rms(out - Eo) < 2e-6
+    with pytest.raises(ValueError):
+        qb.ph.viterbiviterbi(E[:, :5], 10, 4)                                 # N longer than the signal
+    with pytest.raises(NotImplementedError):
+        qb.ph.viterbiviterbi(E, 513, 4)

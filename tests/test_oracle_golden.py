@@ -185,3 +185,19 @@ def test_decisions_and_metrics(golden, tag):
     assert np.max(np.abs(co.soft_l_value_demapper(rx, nb, snr, bm) - g["lv_" + tag])) < tol * max(1.0, np.max(np.abs(g["lv_" + tag])))
     assert np.max(np.abs(co.soft_l_value_demapper(rx, nb, snr, bm, minmax=True) - g["lvmm_" + tag])) < tol * max(1.0, np.max(np.abs(g["lvmm_" + tag])))
     assert np.allclose(co.estimate_snr(rx, g["tx_" + tag], coded), g["est_" + tag], rtol=1e-5 if tag == "c64" else 1e-12)
+
+
+def test_viterbiviterbi(golden):
+    """Viterbi-Viterbi (phaserecovery.py:40-79): the NumPy restatement follows the reference's dtype at every step,
+    so it reproduces the reference's phases to rounding."""
+    g = golden("g11_viterbi")
+    E = g["in_c64"]
+    for N in (10, 11):
+        Eo, ph = co.viterbiviterbi(E, N, 4)
+        assert ph.dtype == np.float32 and ph.shape == (2, E.shape[1] - N + 1)
+        assert np.max(np.abs(ph[1] - g["ph_c64_%d" % N])) < 1e-6 and np.max(np.abs(ph[0] - g["ph0_c64_%d" % N])) < 1e-6
+        assert Eo.dtype == np.complex64 and rms(Eo - g["out_c64_%d" % N]) < 1e-6
+        o = (N - 1) // 2
+        assert not Eo[:, :o].any() and not Eo[:, o + ph.shape[1]:].any()
+    Eo, ph = co.viterbiviterbi(g["in_c128"], 7, 8)
+    assert np.max(np.abs(ph - g["ph_c128"])) < 1e-13 and rms(Eo - g["out_c128"]) < 1e-13
