@@ -205,6 +205,18 @@ int qb_select_angles_dev(int dtype, const void *angles, int64_t p, int64_t A, co
 int qb_select_angles_host(int dtype, const void *angles, int64_t p, int64_t A, const int64_t *idx,
                           int64_t L, void *out);
 
+/* ---- layout of the training kernels --------------------------------------------------------------------
+ * Sets the layout used by the CALLING THREAD's subsequent qb_train_equaliser_dev calls and returns the
+ * previous one.  QB_LAYOUT_THROUGHPUT (default): four streams per warp, the layout that fills the machine
+ * when a launch holds hundreds of (segment, mode) streams.  QB_LAYOUT_LATENCY: one stream per warp (taps
+ * spread over all 32 lanes, warp-wide fixed-point reduction of the tap dot) -- for calls whose time is the
+ * serial depth of a few streams, i.e. the reference's own call shape: train_equaliser on ONE capture
+ * (pythran_equalisation.py:130-173 has one stream per trained mode).  qb_train_equaliser_host always runs
+ * in the latency layout.  The layout is never chosen from the size of a launch, so a stream's result does
+ * not depend on what else shares its launch; both layouts meet the same parity tolerance.                */
+enum { QB_LAYOUT_THROUGHPUT = 0, QB_LAYOUT_LATENCY = 1 };
+int qb_set_train_layout(int layout);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t qb_launch_count(void);
 

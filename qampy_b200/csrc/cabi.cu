@@ -26,6 +26,7 @@ int set_error(int code, const char *fmt, ...)
 }
 void count_launch(int n) { g_launches += n; }
 
+int set_train_layout(int layout);
 int apply_dispatch(int dtype, const void *E, int64_t nseg, int64_t seg_stride, int64_t row_stride,
                    int64_t nmodes, int64_t L, int64_t os, const void *wx, int64_t ntaps,
                    const int64_t *modes, int64_t nsel, void *out, cudaStream_t st);
@@ -190,6 +191,7 @@ extern "C" {
 int qb_version(void) { return QB_VERSION; }
 const char *qb_last_error(void) { return g_err; }
 int64_t qb_launch_count(void) { return g_launches.load(); }
+int qb_set_train_layout(int layout) { return qb::set_train_layout(layout); }
 
 int qb_device_count(void)
 {
@@ -261,6 +263,12 @@ int qb_train_equaliser_host(int dtype, const void *E, int64_t nmodes, int64_t L,
     QB_CUDA_CHECK(cudaMemcpyAsync(dS.p, symbols, nS * cs, cudaMemcpyHostToDevice, st));
     if (err) QB_CUDA_CHECK(cudaMemsetAsync(dErr.p, 0, nErr * cs, st));  // unselected rows stay 0 (:161)
     unsigned char mubuf[QB_MAX_MODES * 8];
+    // one capture, one stream per trained mode: the call takes as long as a stream is deep -> latency layout
+    struct LayoutGuard {
+        int old;
+        LayoutGuard() : old(qb::set_train_layout(QB_LAYOUT_LATENCY)) {}
+        ~LayoutGuard() { qb::set_train_layout(old); }
+    } layout_guard;
     if (!adaptive || !mu_shared || nsel <= 1) {
         for (int64_t j = 0; j < nsel; j++) memcpy(mubuf + j * rs, mu, rs);
         QB_CUDA_CHECK(cudaMemcpyAsync(dMu.p, mubuf, (nsel ? nsel : 1) * rs, cudaMemcpyHostToDevice, st));

@@ -12,8 +12,19 @@
 namespace qb {
 
 int train_la_l8(TrainParams<float> p, cudaStream_t st);
+int train_la_l32(TrainParams<float> p, cudaStream_t st);
 int train_fast_l8(TrainParams<float> p, cudaStream_t st);
 int train_fast_l16(TrainParams<float> p, cudaStream_t st);
+
+// Layout of the calling thread's training launches (qb_set_train_layout): 0 = throughput (fixed 8-lane layout),
+// 1 = latency (one stream per warp where that kernel is instantiated).
+static thread_local int g_train_layout = 0;
+int set_train_layout(int layout)
+{
+    const int old = g_train_layout;
+    g_train_layout = layout ? 1 : 0;
+    return old;
+}
 
 // Returns 1 if the fast path took the job, 0 if the shape is outside it (caller falls back), <0 on error.
 int train_fast_try(TrainParams<float> p, cudaStream_t st)
@@ -31,7 +42,11 @@ int train_fast_try(TrainParams<float> p, cudaStream_t st)
     // stream, 6 or 12 taps per lane.  QB_TRAIN_KERNEL=direct keeps the direct form (tests run both).
     const char *kern = getenv("QB_TRAIN_KERNEL");
     if (!forced && !(kern && kern[0] == 'd')) {
-        const int rc = train_la_l8(p, st);
+        // The layout is the CALLER's choice, never a function of how many streams a launch holds: a stream's
+        // result stays independent of what shares its launch.
+        int rc = g_train_layout == 1 ? train_la_l32(p, st) : 0;
+        if (rc != 0) return rc;
+        rc = train_la_l8(p, st);
         if (rc != 0) return rc;
     }
     int order[2] = {8, 16};

@@ -247,16 +247,16 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                 // ---- 1. all-reduce of the partial Q_il, hops interleaved with W += c_{il-1} conj(X_{il-1}) ----
                 float qr = pqr, qi = pqi;
                 const float ncr = -crp;
-                constexpr int NHOP = LPS == 8 ? 3 : (LPS == 16 ? 4 : 5);
+                if constexpr (LPS == 32) {
+                    // one stream per warp (latency layout): the 32 partials are summed as 8.24 fixed point by ONE
+                    // warp-wide integer reduction each (REDUX) instead of five shuffle hops -- exact integer sum,
+                    // so the result does not depend on the lane order; the tap update hides its latency
+                    const int sr = __reduce_add_sync(0xffffffffu, __float2int_rn(pqr * 16777216.f));
+                    const int si = __reduce_add_sync(0xffffffffu, __float2int_rn(pqi * 16777216.f));
 #pragma unroll
-                for (int h = 0; h < NHOP; h++) {
-                    const int m = LPS >> (h + 1);
-                    const float tr = __shfl_xor_sync(0xffffffffu, qr, m);
-                    const float ti = __shfl_xor_sync(0xffffffffu, qi, m);
-#pragma unroll
-                    for (int q = (NP * h) / NHOP; q < (NP * (h + 1)) / NHOP; q++) {
+                    for (int q = 0; q < NP; q++) {
                         f32x2 xr = XR[(u + q) % B], xi = XI[(u + q) % B];
-                        if (q >= NP - NMASK) {   // taps past ntaps stay exactly zero
+                        if (q >= NP - NMASK) {
                             xr = mul2(xr, MK[q - (NP - NMASK)]);
                             xi = mul2(xi, MK[q - (NP - NMASK)]);
                         }
@@ -265,12 +265,35 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                         PI[q] = fma2_bcast(cip, xr, PI[q]);
                         PI[q] = fma2_bcast(ncr, xi, PI[q]);
                     }
-                    qr += tr;
-                    qi += ti;
+                    // Q + c G with the Gram term formed first: only one FMA follows the reduction
+                    qr = fmaf((float)sr, 1.f / 16777216.f, fmaf(-cip, Gi.y, crp * Gi.x));
+                    qi = fmaf((float)si, 1.f / 16777216.f, fmaf(cip, Gi.x, crp * Gi.y));
+                } else {
+                    constexpr int NHOP = LPS == 8 ? 3 : 4;
+#pragma unroll
+                    for (int h = 0; h < NHOP; h++) {
+                        const int m = LPS >> (h + 1);
+                        const float tr = __shfl_xor_sync(0xffffffffu, qr, m);
+                        const float ti = __shfl_xor_sync(0xffffffffu, qi, m);
+#pragma unroll
+                        for (int q = (NP * h) / NHOP; q < (NP * (h + 1)) / NHOP; q++) {
+                            f32x2 xr = XR[(u + q) % B], xi = XI[(u + q) % B];
+                            if (q >= NP - NMASK) {   // taps past ntaps stay exactly zero
+                                xr = mul2(xr, MK[q - (NP - NMASK)]);
+                                xi = mul2(xi, MK[q - (NP - NMASK)]);
+                            }
+                            PR[q] = fma2_bcast(crp, xr, PR[q]);
+                            PR[q] = fma2_bcast(cip, xi, PR[q]);
+                            PI[q] = fma2_bcast(cip, xr, PI[q]);
+                            PI[q] = fma2_bcast(ncr, xi, PI[q]);
+                        }
+                        qr += tr;
+                        qi += ti;
+                    }
                 }
                 // ---- 2. y = Q + c_{il-1} G -> error -> c_il, interleaved with the partial dot Q_{il+1} ---------
-                const float yr = fmaf(-cip, Gi.y, fmaf(crp, Gi.x, qr));
-                const float yi = fmaf(cip, Gi.x, fmaf(crp, Gi.y, qi));
+                const float yr = LPS == 32 ? qr : fmaf(-cip, Gi.y, fmaf(crp, Gi.x, qr));
+                const float yi = LPS == 32 ? qi : fmaf(cip, Gi.x, fmaf(crp, Gi.y, qi));
                 f32x2 a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
 #pragma unroll
                 for (int q = 0; q < NP; q++) {
@@ -339,7 +362,9 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     g.lpp = LPS / p.nmodes;
     int nq = (p.ntaps + g.lpp - 1) / g.lpp;
     nq += nq & 1;
-    if (nq != 6 && nq != 12) return 0;       // instantiated shapes (ntaps 21 / 45 dual polarisation, ...)
+    // instantiated shapes: 6 / 12 taps per lane with 8 lanes per stream (ntaps 21 / 45 dual polarisation, ...),
+    // 2 / 4 with one stream per warp (the latency layout)
+    if (LPS == 32 ? (nq != 2 && nq != 4) : (nq != 6 && nq != 12)) return 0;
     const int B = nq / 2 + 2;
     g.tile_syms = (128 / B) * B;              // per-tile costs (loader set-up, window preload) amortised over 128 symbols
     g.pitch = 2 * (g.tile_syms + 1) + g.lpp * nq;

@@ -50,9 +50,14 @@ def segment_view(E, nseg, seg_out_symbols, os, ntaps):
     return E.as_strided((nseg, nmodes, L_seg), (step, E.stride(0), 1), E.storage_offset())
 
 
-def train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, method, err=None):
+_LAYOUTS = {"throughput": 0, "latency": 1}     # qb_set_train_layout (include/qampy_b200.h)
+
+
+def train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, method, err=None, layout="throughput"):
     """Train ``nseg`` independent segments.  ``wx`` (nseg, nmodes, nmodes, ntaps) and ``mu``
-    (nseg, nsel) are updated in place; ``err`` (nseg, nmodes, TrSyms*Niter) is optional."""
+    (nseg, nsel) are updated in place; ``err`` (nseg, nmodes, TrSyms*Niter) is optional.
+    ``layout``: "throughput" (default, batched segments) or "latency" (one stream per warp: calls on ONE
+    capture, whose time is the serial depth of a stream; ``qb_set_train_layout`` in the header)."""
     if method not in _lib.METHODS:
         raise ValueError("Unknown method %s" % method)
     _check_cuda(E, wx, mu, symbols, err)
@@ -67,10 +72,15 @@ def train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, meth
         assert (TrSyms - 1) * os + ntaps <= L, "Field must be longer than the number of training symbols"
     if err is not None:
         assert err.is_contiguous() and err.shape == (nseg, nmodes, TrSyms * Niter) and err.dtype == E.dtype
-    _lib.check(_lib.load().qb_train_equaliser_dev(
-        _CODE[E.dtype], _ptr(E), nseg, E.stride(0), E.stride(1), nmodes, int(TrSyms), int(Niter), int(os),
-        _ptr(wx), ntaps, mp, modes.size, int(bool(adaptive)), _ptr(symbols), symbols.shape[1],
-        _lib.METHODS[method], _ptr(mu), _ptr(err), _stream()))
+    lib = _lib.load()
+    old = lib.qb_set_train_layout(_LAYOUTS[layout])
+    try:
+        _lib.check(lib.qb_train_equaliser_dev(
+            _CODE[E.dtype], _ptr(E), nseg, E.stride(0), E.stride(1), nmodes, int(TrSyms), int(Niter), int(os),
+            _ptr(wx), ntaps, mp, modes.size, int(bool(adaptive)), _ptr(symbols), symbols.shape[1],
+            _lib.METHODS[method], _ptr(mu), _ptr(err), _stream()))
+    finally:
+        lib.qb_set_train_layout(old)
     return err, wx, mu
 
 

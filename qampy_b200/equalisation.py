@@ -60,7 +60,8 @@ def apply_filter(E, os, wxy, method="pyt", modes=None):
 
 def _train_stage(Ed, os, mu, M, wd, ntaps, TrSyms, Niter, method, adaptive, symbols, modes, cdtype,
                  mu_shared=True):
-    """One equalise_signal training stage on device tensors (nseg = 1).  Returns err (numpy)."""
+    """One equalise_signal training stage on device tensors (nseg = 1: the reference's own call on one capture,
+    one serial stream per trained mode -> the latency layout of the training kernels).  Returns err (numpy)."""
     dev = Ed.device
     nmodes, L = Ed.shape[1], Ed.shape[2]
     rt = np.float32 if cdtype == np.complex64 else np.float64
@@ -74,10 +75,10 @@ def _train_stage(Ed, os, mu, M, wd, ntaps, TrSyms, Niter, method, adaptive, symb
         # the reference carries ONE step size through the modes in list order when interpreted
         mud = torch.full((1, 1), float(mu), dtype=device._REAL[Ed.dtype], device=dev)
         for m in modes:
-            device.train_equaliser(Ed, TrSyms, Niter, os, mud, wd, [m], adaptive, sd, method, err)
+            device.train_equaliser(Ed, TrSyms, Niter, os, mud, wd, [m], adaptive, sd, method, err, layout="latency")
     else:
         mud = torch.full((1, len(modes)), float(mu), dtype=device._REAL[Ed.dtype], device=dev)
-        device.train_equaliser(Ed, TrSyms, Niter, os, mud, wd, modes, adaptive, sd, method, err)
+        device.train_equaliser(Ed, TrSyms, Niter, os, mud, wd, modes, adaptive, sd, method, err, layout="latency")
     return err
 
 

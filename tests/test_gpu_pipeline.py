@@ -27,17 +27,18 @@ def env():
     return ns
 
 
-@pytest.mark.parametrize("kernel", ["la8", "lps8", "lps16", "warp"])
+@pytest.mark.parametrize("kernel", ["la8", "la32", "lps8", "lps16", "warp"])
 @pytest.mark.parametrize("M,ntaps,nmodes", [(64, 45, 2), (16, 21, 2), (4, 11, 1), (16, 17, 2), (64, 64, 2)])
 def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypatch):
-    """Every training kernel (look-ahead; direct planar/packed with 8 or 16 lanes per stream; generic warp per
+    """Every training kernel (look-ahead in the throughput layout and in the latency layout = one stream per warp
+    with the fixed-point warp reduction; direct planar/packed with 8 or 16 lanes per stream; generic warp per
     stream) on 3 segments, all error functions with a dedicated code path."""
     import qampy_b200.pythran_equalisation as pe
     for var in ("QB_TRAIN_KERNEL", "QB_TRAIN_LPS"):
         monkeypatch.delenv(var, raising=False)
     if kernel == "warp":
         monkeypatch.setenv("QB_TRAIN_KERNEL", "warp")
-    elif kernel != "la8":                              # la8 = default: look-ahead form where instantiated
+    elif kernel not in ("la8", "la32"):                # la8 = default: look-ahead form where instantiated
         monkeypatch.setenv("QB_TRAIN_LPS", kernel[3:])  # direct form, 8 or 16 lanes per stream
     E, _ = env.synth.synth_numpy(M, 5000, nmodes=nmodes, seed=M + ntaps, snr_db=24.0)
     t = env.torch
@@ -51,13 +52,42 @@ def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypa
         w = t.from_numpy(np.tile(env.theory.init_taps(ntaps, nmodes, np.complex64), (nseg, 1, 1, 1))).to(env.dev)
         mu = t.full((nseg, nmodes), 2e-3, dtype=t.float32, device=env.dev)
         err = t.zeros((nseg, nmodes, tr), dtype=t.complex64, device=env.dev)
-        env.device.train_equaliser(Ev, tr, 1, 2, mu, w, None, False, t.from_numpy(sy).to(env.dev), method, err)
+        env.device.train_equaliser(Ev, tr, 1, 2, mu, w, None, False, t.from_numpy(sy).to(env.dev), method, err,
+                                   layout="latency" if kernel == "la32" else "throughput")
         Es = np.stack([E[:, s * S * 2: s * S * 2 + L_seg] for s in range(nseg)])
         wr = np.tile(env.theory.init_taps(ntaps, nmodes, np.complex64), (nseg, 1, 1, 1))
         er, wr, _ = env.co.train_segments(Es, tr, 1, 2, 2e-3, wr, np.arange(nmodes), False, sy, method,
                                           mu_shared=False)
         assert rms(err.cpu().numpy() - er) < 1e-5 * max(1.0, rms(er)), (method, kernel)
         assert np.max(np.abs(w.cpu().numpy() - wr)) < 2e-5, (method, kernel)
+
+
+def test_train_layout_is_the_callers_choice(env):
+    """qb_set_train_layout: per-thread, returns the previous value; the latency layout (one stream per warp,
+    fixed-point warp reduction) really is another kernel -- same results to rounding, not bit for bit -- and in
+    either layout a stream's result does not depend on how many streams share the launch."""
+    from qampy_b200 import _lib
+    lib, t = _lib.load(), env.torch
+    assert lib.qb_set_train_layout(1) == 0 and lib.qb_set_train_layout(0) == 1 and lib.qb_set_train_layout(0) == 0
+    M, ntaps, nseg, S = 64, 45, 5, 1200
+    E, _ = env.synth.synth_numpy(M, nseg * S + 100, seed=77, snr_db=26.0)
+    Ev = env.device.segment_view(t.from_numpy(E).to(env.dev), nseg, S, 2, ntaps)
+    tr = env.theory.cal_training_symbol_len(2, ntaps, Ev.shape[2])
+    sy = t.from_numpy(env.theory.reshape_symbols(None, "mcma", M, np.complex64, 2)).to(env.dev)
+    res = {}
+    for layout in ("throughput", "latency"):
+        for sel in (slice(0, nseg), slice(2, 3)):
+            n = sel.stop - sel.start
+            w = t.from_numpy(np.tile(env.theory.init_taps(ntaps, 2, np.complex64), (n, 1, 1, 1))).to(env.dev)
+            mu = t.full((n, 2), 1e-3, dtype=t.float32, device=env.dev)
+            err = t.zeros((n, 2, tr), dtype=t.complex64, device=env.dev)
+            env.device.train_equaliser(Ev[sel], tr, 1, 2, mu, w, None, False, sy, "mcma", err, layout=layout)
+            res[layout, n] = (w.cpu().numpy(), err.cpu().numpy())
+        assert np.array_equal(res[layout, nseg][0][2], res[layout, 1][0][0])       # segment 2 alone == in the batch
+        assert np.array_equal(res[layout, nseg][1][2], res[layout, 1][1][0])
+    a, b = res["throughput", nseg], res["latency", nseg]
+    assert not np.array_equal(a[0], b[0])
+    assert np.max(np.abs(a[0] - b[0])) < 1e-5 and rms(a[1] - b[1]) < 1e-5
 
 
 def test_segmented_pipeline_equals_reference_per_segment(env):
