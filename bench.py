@@ -40,6 +40,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3 (default, the contract's N=1 workload): --nsym symbols per GPU, weak scaling; c5: BASELINE "
+                         "config 5, ONE capture of 5e8 symbols per polarisation (1e9 samples) cut into contiguous "
+                         "per-rank ranges of whole segments (strong scaling, no collective)")
     ap.add_argument("--nsym", type=int, default=10 ** 7, help="symbols per polarisation per GPU")
     ap.add_argument("--seg", type=int, default=-1,
                     help="output symbols per segment; -1 = smallest length >= 8192 that fills whole GPU waves "
@@ -56,12 +60,15 @@ def parse():
 
 
 def workload_config(a, world):
-    return {"workload": "C3 dual-pol %d-QAM dual_mode_equalisation(mcma->mrde, ntaps=%d, mu=1e-3) + bps(%d, N=%d), "
-                        "2 sps, %d symbols per GPU" % (a.M, a.ntaps, a.angles, a.bpsN, a.nsym),
+    name = "C3" if a.workload == "c3" else "C5 (1e9-sample capture over %d GPU(s))" % world
+    return {"workload": "%s dual-pol %d-QAM dual_mode_equalisation(mcma->mrde, ntaps=%d, mu=1e-3) + bps(%d, N=%d), "
+                        "2 sps, %d symbols per GPU" % (name, a.M, a.ntaps, a.angles, a.bpsN, a.nsym),
             "symbols_per_gpu": a.nsym, "samples_per_gpu": 2 * a.nsym, "segment_symbols": a.seg or a.nsym,
             "segment_semantics": "each segment == reference call on that segment (centre-spike taps)",
-            "sharding": "dp%d (independent captures per rank, no collective)" % world,
-            "l2_policy": "inputs (320 MB/GPU) larger than L2 (126 MB); no explicit flush"}
+            "sharding": ("dp%d (independent captures per rank, no collective)" % world) if a.workload == "c3" else
+                        ("dp%d (every rank synthesises and processes its own contiguous range of %d symbols of the "
+                         "5e8-symbol capture; whole segments, no collective)" % (world, a.nsym)),
+            "l2_policy": "inputs (%d MB/GPU) larger than L2 (126 MB); no explicit flush" % (a.nsym * 32 // 10 ** 6)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -247,6 +254,9 @@ def run_b200(a, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     _lib.require_device()
     if world > 1:
+        # the one stdout line of this script is the JSON line: keep NCCL's version banner out of it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -258,7 +268,10 @@ def run_b200(a, rank, local_rank, world):
                                   bps_angles=a.angles, bps_N=a.bpsN, seg_symbols=a.seg or None)
     rx = pipeline.SegmentedReceiver(cfg, dev)
     rx.want_idx = False
-    E, syms = synth.synth_signal(a.M, a.nsym, seed=1000 + rank, snr_db=28.0, device=dev)
+    if a.nsym > 2 * 10 ** 7:    # long captures are synthesised block by block (double-precision FFT temporaries)
+        E, syms = synth.synth_capture(a.M, a.nsym, seed=1000 + 100 * rank, snr_db=28.0, device=dev)
+    else:
+        E, syms = synth.synth_signal(a.M, a.nsym, seed=1000 + rank, snr_db=28.0, device=dev)
     L = E.shape[1]
     groups = pipeline.plan_segments(L, cfg)
     nsym_out = sum(n * k for _, n, k, _ in groups)
@@ -374,7 +387,8 @@ def run_b200(a, rank, local_rank, world):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak" if a.workload == "c3" else "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "msymbols_per_s": value / 2, "sanity": {"eq_out_rms": out_rms, "ser_segment0": ser}}
@@ -390,6 +404,12 @@ def run_b200(a, rank, local_rank, world):
 
 def resolve_segments(a):
     """--seg -1: balanced segment length for this capture (same value for the GPU and the CPU arm)."""
+    if a.workload == "c5":
+        # one capture of 5e8 symbols per polarisation; every rank holds the samples of its own contiguous range of
+        # whole segments (pipeline.rank_capture_range: ntaps-1 samples of overlap with its neighbour, no exchange)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        a.nsym = 5 * 10 ** 8 // world
+        a.no_e2e = True            # a 16 GB pinned host capture is not part of this mode
     if a.seg < 0:
         from qampy_b200 import pipeline
         cfg = pipeline.ReceiverConfig(M=a.M, ntaps=a.ntaps, os=2)

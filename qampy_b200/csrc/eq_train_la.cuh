@@ -24,6 +24,8 @@
 // The register window holds NP + 2 pairs per plane because symbol i needs the windows of symbols i-1
 // (update) and i+1 (dot); tiles are staged from one pair (2 samples) before the tile's first symbol.
 #pragma once
+#include <algorithm>
+
 #include "eq_train_fast.cuh"
 
 namespace qb {
@@ -38,13 +40,17 @@ namespace qb {
 // a running sum over <= 416 products (<= 3e-5 absolute) is far below the fp32 resolution of y.
 constexpr int GRAM_CH = 13;   // 32 * 13 = 416 >= 2 * 128 + 8 * 12 + 2 products per tile
 
+// entries of the running sum a tile needs: S[2 il + ntaps] for il < tile_syms
+__host__ __device__ __forceinline__ int gram_sum_len(int tile_syms, int ntaps) { return 2 * (tile_syms - 1) + ntaps + 1; }
+
 __device__ __forceinline__ void tile_gram(const float *tile, int nslots, int nmodes, int pitch, int tile_syms,
                                           int ntaps, float2 *S, float2 *gbuf, int lane)
 {
+    const int slen = gram_sum_len(tile_syms, ntaps);
     const int row_floats = 2 * pitch, slot_floats = nmodes * row_floats;
     for (int sl = 0; sl < nslots; sl++) {
         const float *base = tile + sl * slot_floats;
-        float2 *Ss = S + sl * (32 * GRAM_CH + 1);
+        float2 *Ss = S + sl * slen;
         const int mb = 2 + lane * GRAM_CH;
         // products beyond mend read whatever follows in shared memory; running sums are causal, so they only
         // reach entries of S that nobody reads -- no bounds branch in here
@@ -86,8 +92,10 @@ __device__ __forceinline__ void tile_gram(const float *tile, int nslots, int nmo
         off.x -= run.x;
         off.y -= run.y;
         if (lane == 0) Ss[0] = make_float2(0.f, 0.f);
+        // only S[0 .. 2 (tile_syms - 1) + ntaps] is ever read (and allocated: gram_sum_len)
 #pragma unroll
-        for (int j = 0; j < GRAM_CH; j++) Ss[mb + j - 1] = make_float2(off.x + loc[j].x, off.y + loc[j].y);
+        for (int j = 0; j < GRAM_CH; j++)
+            if (mb + j - 1 < slen) Ss[mb + j - 1] = make_float2(off.x + loc[j].x, off.y + loc[j].y);
         __syncwarp();
         for (int il = lane; il < tile_syms; il += 32) {
             const float2 hi = Ss[2 * il + ntaps], lo = Ss[2 * il];
@@ -129,9 +137,13 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     float *tile0 = reinterpret_cast<float *>(smem_raw);
     float *tile1 = tile0 + g.nslots * slot_floats;
     float2 *gbuf = reinterpret_cast<float2 *>(tile1 + g.nslots * slot_floats);
+    // The running sums live only inside tile_gram (start of a tile), the error buffer is filled by the symbol loop
+    // and flushed at the end of the tile: they share one region, which keeps a warp's slice small enough for
+    // 8 warps per SM when a launch holds more than one wave of streams (long captures).
     float2 *gsum = gbuf + g.nslots * g.tile_syms;
-    float2 *errs = gsum + g.nslots * (32 * GRAM_CH + 1);   // [GPW][tile_syms]
-    float2 *syms = errs + GPW * g.tile_syms;         // [GPW][nsym_smem]
+    float2 *errs = gsum;                                    // [GPW][tile_syms]
+    const int shared_len = max(g.nslots * gram_sum_len(g.tile_syms, p.ntaps), GPW * g.tile_syms);
+    float2 *syms = gsum + shared_len;                       // [GPW][nsym_smem]
 
     const float2 *gsyms = p.symbols + (long long)mode * p.K;
     float2 *mysyms = syms + grp * p.nsym_smem;
@@ -371,9 +383,9 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     g.nslots = (GPW % p.nsel == 0) ? GPW / p.nsel : (GPW / p.nsel + 2 < GPW ? GPW / p.nsel + 2 : GPW);
     if (g.nslots < 1) g.nslots = 1;
     if (2 * g.tile_syms + g.lpp * nq + 2 > 32 * GRAM_CH) return 0;
-    smem = ((size_t)2 * g.nslots * p.nmodes * g.pitch + (size_t)g.nslots * g.tile_syms +
-            (size_t)g.nslots * (32 * GRAM_CH + 1) + (size_t)GPW * g.tile_syms + (size_t)GPW * p.nsym_smem) *
-           sizeof(float2);
+    const size_t shared_len = std::max((size_t)g.nslots * gram_sum_len(g.tile_syms, p.ntaps), (size_t)GPW * g.tile_syms);
+    smem = ((size_t)2 * g.nslots * p.nmodes * g.pitch + (size_t)g.nslots * g.tile_syms + shared_len +
+            (size_t)GPW * p.nsym_smem) * sizeof(float2);
     if (smem > 56 * 1024) return 0;   // four warp slices per CTA must fit 227 kB
     return nq;
 }
@@ -391,7 +403,10 @@ static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem
     const long long nblk = (p.nstreams + GPW - 1) / GPW;
     const size_t wsm = (smem + 15) & ~(size_t)15;   // per-warp slice, 16-byte aligned
     const int wpb = (int)(train_warps_per_cta(nblk) < nblk ? train_warps_per_cta(nblk) : nblk);   // never more warps (or shared memory) than streams need
-    train_la_kernel<LPS, NQ, METHOD, NMASK><<<(unsigned)((nblk + wpb - 1) / wpb), 32 * wpb, wpb * wsm, st>>>(p, g, (int)wsm);
+    // multi-warp CTAs (small launches) ask for more than half of an SM's shared memory so that ONE of them fits an
+    // SM and concurrent launches spread over the machine (eq_train_fast.cuh, TRAIN_WPB)
+    const size_t dyn = wpb > 1 ? std::max((size_t)wpb * wsm, (size_t)116 * 1024) : wsm;
+    train_la_kernel<LPS, NQ, METHOD, NMASK><<<(unsigned)((nblk + wpb - 1) / wpb), 32 * wpb, dyn, st>>>(p, g, (int)wsm);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;

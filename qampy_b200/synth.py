@@ -119,6 +119,26 @@ def synth_pilot_signal(M, frame_len, pilot_seq_len, pilot_ins_rat, nframes, nmod
                 ph_pilots=pilots[:, pilot_seq_len:].to(dtype), idx_pil=idx_pil)
 
 
+def synth_capture(M, nsym, block=10 ** 7, seed=0, device="cpu", dtype=torch.complex64, **kwargs):
+    """Long capture (BASELINE config C5: 1e9 samples) written block by block into one preallocated array: every block
+    of ``block`` symbols is an independent :func:`synth_signal` realisation (seed + block index), so the FFT-based
+    channel never needs more than one block of double-precision temporaries.  Blocks are not continuous with each
+    other; segments are trained independently anyway and one in ``block / segment`` sees a boundary.
+    Returns ``(E, symbols_of_block_0)``."""
+    os_ = int(kwargs.get("os", 2))
+    nmodes = int(kwargs.get("nmodes", 2))
+    E = torch.empty((nmodes, nsym * os_), dtype=dtype, device=device)
+    syms0 = None
+    for b, a in enumerate(range(0, nsym, block)):
+        n = min(block, nsym - a)
+        Eb, sb = synth_signal(M, n, seed=seed + b, device=device, dtype=dtype, **kwargs)
+        E[:, a * os_:(a + n) * os_] = Eb
+        if syms0 is None:
+            syms0 = sb
+        del Eb, sb
+    return E, syms0
+
+
 def apply_phase_noise(x, linewidth, fs, seed=0):
     """Wiener phase walk with variance 2*pi*linewidth/fs per sample, independent per row."""
     gen = torch.Generator(device=x.device)

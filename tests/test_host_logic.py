@@ -144,3 +144,16 @@ def test_patch_wires_both_seams_and_restores():
     assert cph.bps is orig[2]
     with pytest.raises(ValueError):
         patch.patch("l3")
+
+
+def test_synth_capture_is_blockwise_synth_signal():
+    """Long captures (BASELINE config C5) are synthesised block by block: block b == synth_signal(seed + b)."""
+    import torch
+    from qampy_b200 import synth
+    E, s0 = synth.synth_capture(16, 2500, block=1000, seed=7, snr_db=25.0)
+    assert E.shape == (2, 5000) and E.dtype == torch.complex64 and s0.shape == (2, 1000)
+    for b, (a, n) in enumerate(((0, 1000), (1000, 1000), (2000, 500))):
+        Eb, sb = synth.synth_signal(16, n, seed=7 + b, snr_db=25.0)
+        assert torch.equal(E[:, 2 * a:2 * (a + n)], Eb)
+        if b == 0:
+            assert torch.equal(s0, sb)
