@@ -276,3 +276,49 @@ def test_full_size_c2_properties(env):
     Eb, phr = env.co.bps_driver(g["eq"][s].cpu().numpy(), A, alphabet, N)
     assert np.array_equal(g["ph"][s].cpu().numpy(), phr) and rms(g["out"][s].cpu().numpy() - Eb) < 1e-6
     assert 0.6 < rms(g["eq"].cpu().numpy()) < 1.2            # not collapsed (4096-symbol segments: MCMA still converging)
+
+
+def test_dev_entry_points_are_cuda_graph_capturable(env):
+    """The ``*_dev`` entry points only enqueue on the caller's stream (no synchronisation, no allocation), so a whole
+    train -> train -> apply -> bps chain can be captured in a CUDA graph and replayed on new data in place."""
+    t, dv = env.torch, env.device
+    M, ntaps, nseg, S = 64, 45, 6, 1100
+    cfg = env.pipeline.ReceiverConfig(M=M, ntaps=ntaps, seg_symbols=S)
+    E1, _ = env.synth.synth_signal(M, nseg * S + 50, seed=21, snr_db=27.0, device=env.dev)
+    E2, _ = env.synth.synth_signal(M, nseg * S + 50, seed=22, snr_db=27.0, device=env.dev)
+    Ebuf = E1.clone()
+    Ev = dv.segment_view(Ebuf, nseg, S, 2, ntaps)
+    tr = env.theory.cal_training_symbol_len(2, ntaps, Ev.shape[2])
+    syms = [t.from_numpy(env.theory.reshape_symbols(None, m, M, np.complex64, 2)).to(env.dev) for m in ("mcma", "mrde")]
+    tabs = dv.BpsTables(64, env.theory.normalised_symbols(M).astype(np.complex64), np.complex64, env.dev)
+    w0 = t.from_numpy(np.tile(env.theory.init_taps(ntaps, 2, np.complex64), (nseg, 1, 1, 1))).to(env.dev)
+    w, mu = w0.clone(), t.empty((nseg, 2), dtype=t.float32, device=env.dev)
+    eq = t.empty((nseg, 2, S), dtype=t.complex64, device=env.dev)
+    keep = {}
+
+    def chain():
+        w.copy_(w0)
+        for st in range(2):
+            mu.fill_(1e-3)
+            dv.train_equaliser(Ev, tr, 1, 2, mu, w, None, False, syms[st], ("mcma", "mrde")[st], None)
+        dv.apply_filter_to_signal(Ev, 2, w, out=eq)
+        keep["out"], keep["ph"], _ = dv.bps(eq.reshape(nseg * 2, S), tabs, 45, want_idx=False)
+
+    chain()                                   # warm-up: one-time function attributes are set outside the capture
+    t.cuda.synchronize()
+    ref1 = (keep["out"].clone(), keep["ph"].clone(), w.clone())
+    g = t.cuda.CUDAGraph()
+    with t.cuda.graph(g):
+        chain()
+    out_g, ph_g = keep["out"], keep["ph"]     # static outputs of the captured chain
+    g.replay()
+    t.cuda.synchronize()
+    assert t.equal(out_g, ref1[0]) and t.equal(ph_g, ref1[1]) and t.equal(w, ref1[2])
+    Ebuf.copy_(E2)                            # new capture, same graph
+    g.replay()
+    t.cuda.synchronize()
+    got = (out_g.clone(), ph_g.clone(), w.clone())
+    chain()
+    t.cuda.synchronize()
+    assert t.equal(got[0], keep["out"]) and t.equal(got[1], keep["ph"]) and t.equal(got[2], w)
+    assert not t.equal(got[0], ref1[0])
