@@ -67,7 +67,7 @@ def _train_stage(Ed, os, mu, M, wd, ntaps, TrSyms, Niter, method, adaptive, symb
     rt = np.float32 if cdtype == np.complex64 else np.float64
     if TrSyms is None:
         TrSyms = theory.cal_training_symbol_len(os, ntaps, L)
-    symbols = theory.reshape_symbols(symbols, method, M, cdtype, nmodes)
+    symbols = theory.unique_alphabet(theory.reshape_symbols(symbols, method, M, cdtype, nmodes), method)
     sd = _to_dev(symbols, dev)
     err = torch.zeros((1, nmodes, TrSyms * Niter), dtype=Ed.dtype, device=dev)
     mu = rt(mu)
@@ -129,8 +129,11 @@ def equalise_signal(E, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, me
     return wxy, err
 
 
+SUPPORTS_RETURN_ERR = True      # equalise_windows(return_err=False): callers that only want the taps (pilots.py)
+
+
 def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=None, Niter=1, method="mcma",
-                     adaptive_stepsize=False, symbols=None, modes=None, apply=False, **kwargs):
+                     adaptive_stepsize=False, symbols=None, modes=None, apply=False, return_err=True, **kwargs):
     """``equalise_signal(E[:, s:s + window], os, mu, M, wxy=..., ...)`` for every ``s`` in ``starts`` as ONE batched
     launch per stage: the windows are strided views of the capture on the device, one segment per window.
 
@@ -142,7 +145,9 @@ def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=
     ``E``: NumPy array or CUDA tensor (nmodes, L).  ``wxy``: None (centre spike), (nmodes, nmodes, Ntaps)
     shared by all windows, or (nwin, nmodes, nmodes, Ntaps).  ``symbols``: as for ``equalise_signal``, shared
     by all windows.  Returns ``(wxy (nwin, nmodes, nmodes, Ntaps), err (nwin, nmodes, TrSyms*Niter))`` and, with
-    ``apply``, the equalised windows ``(nwin, len(modes), (window - Ntaps + 1)//os)`` first -- NumPy arrays."""
+    ``apply``, the equalised windows ``(nwin, len(modes), (window - Ntaps + 1)//os)`` first -- NumPy arrays.
+    ``return_err=False``: the per-symbol error is neither stored nor copied back (``err`` is None): the pilot
+    equaliser trains Niter = 30 passes per stage and only ever looks at the taps."""
     starts = np.atleast_1d(np.asarray(starts, dtype=np.int64))
     method_l = method.lower()
     if method_l in REAL_VALUED or (starts.size > 1 and np.unique(np.diff(starts)).size > 1):
@@ -188,8 +193,8 @@ def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=
     rt = np.float32 if cdtype == np.complex64 else np.float64
     if TrSyms is None:
         TrSyms = theory.cal_training_symbol_len(int(os), Ntaps, int(window))
-    sd = _to_dev(theory.reshape_symbols(symbols, method_l, M, cdtype.type, nmodes), dev)
-    err = torch.zeros((nwin, nmodes, TrSyms * int(Niter)), dtype=Ed.dtype, device=dev)
+    sd = _to_dev(theory.unique_alphabet(theory.reshape_symbols(symbols, method_l, M, cdtype.type, nmodes), method_l), dev)
+    err = torch.zeros((nwin, nmodes, TrSyms * int(Niter)), dtype=Ed.dtype, device=dev) if return_err else None
     mu = float(rt(mu))
     if adaptive_stepsize and kwargs.get("mu_shared", True) and len(modes) > 1:
         mud = torch.full((nwin, 1), mu, dtype=device._REAL[Ed.dtype], device=dev)   # one step size per window,
@@ -198,7 +203,7 @@ def equalise_windows(E, starts, window, os, mu, M, wxy=None, Ntaps=None, TrSyms=
     else:
         mud = torch.full((nwin, len(modes)), mu, dtype=device._REAL[Ed.dtype], device=dev)
         device.train_equaliser(Ev, TrSyms, int(Niter), int(os), mud, wd, modes, adaptive_stepsize, sd, method_l, err)
-    res = (wd.cpu().numpy(), err.cpu().numpy())
+    res = (wd.cpu().numpy(), err.cpu().numpy() if return_err else None)
     if apply:
         out = device.apply_filter_to_signal(Ev, int(os), wd, modes)
         return (out.cpu().numpy(),) + res

@@ -33,6 +33,14 @@ def patch(level="l2"):
     ceq = importlib.import_module("qampy.core.equalisation.equalisation")
     cph = importlib.import_module("qampy.core.phaserecovery")
     ref_pe = importlib.import_module("qampy.core.equalisation.pythran_equalisation")
+    # import every module that from-imports the kernels BEFORE the first attribute is replaced: a module imported
+    # while its source is already patched would copy the replacement and "restore" to it
+    users = []
+    for modname in ("qampy.core.signal_quality", "qampy.signals"):
+        try:
+            users.append(importlib.import_module(modname))
+        except Exception:
+            continue
     if level == "l1":
         _set(ref_pe, "train_equaliser", q_pe.train_equaliser)
         _set(ref_pe, "train_equaliser_realvalued", q_pe.train_equaliser_realvalued)
@@ -41,11 +49,7 @@ def patch(level="l2"):
         _set(cph, "select_angles", q_dsp.select_angles)
         # decisions and quality metrics are from-imported by the modules that use them
         # (qampy/core/signal_quality.py:26-29, qampy/signals.py:48-49)
-        for modname in ("qampy.core.signal_quality", "qampy.signals"):
-            try:
-                mod = importlib.import_module(modname)
-            except Exception:
-                continue
+        for mod in users:
             for name, fn in (("make_decision", q_pe.make_decision), ("estimate_snr", q_dsp.estimate_snr),
                              ("soft_l_value_demapper", q_dsp.soft_l_value_demapper),
                              ("soft_l_value_demapper_minmax", q_dsp.soft_l_value_demapper_minmax)):

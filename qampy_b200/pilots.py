@@ -392,18 +392,20 @@ def _pilot_frames_batched(be, rx_signal, pilot_seq, shiftfctrs, os, frame_len, m
     per_mode = np.unique(train_shifts).shape[0] > 1
     groups = [(train_shifts[i], [i]) for i in range(npols)] if per_mode else [(train_shifts[0], None)]
     wx = wxinit
+    # only the taps are used: skip storing / downloading Niter * TrSyms errors per window where the backend can
+    noerr = {"return_err": False} if getattr(be, "SUPPORTS_RETURN_ERR", False) else {}
     for start, modes in groups:                 # step 1: blind pre-convergence from the initial taps
         wx, _ = be.equalise_windows(rx_signal, start + foff, span, os, mu[0], M_pilot,
                                     wxy=wx if per_mode else wxinit, Ntaps=Ntaps, Niter=Niter, method=methods[0],
-                                    adaptive_stepsize=adaptive_stepsize, modes=modes)
+                                    adaptive_stepsize=adaptive_stepsize, modes=modes, **noerr)
     taps = wx
     for start, modes in groups:                 # step 2: both methods with the pilot sequence as training symbols
         taps, _ = be.equalise_windows(rx_signal, start + foff, span, os, mu[0], M_pilot, wxy=taps, Ntaps=Ntaps,
                                       Niter=Niter, method=methods[0], adaptive_stepsize=adaptive_stepsize,
-                                      symbols=ref, modes=modes)
+                                      symbols=ref, modes=modes, **noerr)
         taps, _ = be.equalise_windows(rx_signal, start + foff, span, os, mu[1], 4 if per_mode else M_pilot, wxy=taps,
                                       Ntaps=Ntaps, Niter=Niter, method=methods[1],
-                                      adaptive_stepsize=adaptive_stepsize, symbols=ref, modes=modes)
+                                      adaptive_stepsize=adaptive_stepsize, symbols=ref, modes=modes, **noerr)
     if not apply:
         return taps, None
     ashifts = shifts - (Ntaps - synctaps) // 2 if Ntaps != synctaps else shifts.copy()
@@ -508,10 +510,12 @@ def pilot_receiver(rx_signal, pilot_seq, ph_pilots, idx_pil, frame_len, os, fram
     dev = torch.device("cuda", torch.cuda.current_device())
     rx_host = None if torch.is_tensor(rx_signal) else np.atleast_2d(np.asarray(rx_signal))
     Ed = rx_signal.to(dev) if torch.is_tensor(rx_signal) else torch.from_numpy(np.ascontiguousarray(rx_host)).to(dev)
-    if rx_host is None:
-        rx_host = Ed.cpu().numpy()
     pilot_seq = np.atleast_2d(pilot_seq)
     sl = pilot_seq.shape[-1]
+    if rx_host is None:
+        # capture already on the GPU: the frame search looks at one frame plus two window lengths and takes a
+        # 4k-sample stretch of it on the host -- download that much, not the capture
+        rx_host = Ed[:, :min(Ed.shape[1], (frame_len + 4 * sl) * os)].cpu().numpy()
     # sync2frame (signals.py:1709-1741)
     eqargs = {"adaptive_stepsize": True, "Niter": 10, "method": "cma", "Ntaps": 17, "mu": 5e-3}
     eqargs.update(sync_kwargs or {})

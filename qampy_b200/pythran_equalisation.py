@@ -14,6 +14,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
+from .theory import unique_alphabet
 
 
 def _ctype(dtype):
@@ -58,6 +59,8 @@ def train_equaliser(E, TrSyms, Niter, os, mu, wx, modes, adaptive, symbols, meth
         "wx needs to have at least as many dimensions as the maximum mode"
     symbols = np.ascontiguousarray(symbols, dtype=ct)
     assert symbols.ndim == 2 and symbols.shape[0] == nmodes, "symbols must be at least size of modes"
+    # searched alphabets without their repeats: same decisions, shorter search (theory.unique_alphabet)
+    symbols = np.ascontiguousarray(unique_alphabet(symbols, method))
     modes = np.ascontiguousarray(np.atleast_1d(modes), dtype=np.int64)
     TrSyms, Niter, os = int(TrSyms), int(Niter), int(os)
     err = np.zeros((nmodes, TrSyms * Niter), dtype=ct)

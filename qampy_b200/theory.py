@@ -101,6 +101,30 @@ def generate_symbols_for_eq(method, M, dtype):
     raise ValueError("%s is unknown method" % method)
 
 
+SEARCHED_ALPHABET = ("sbd", "mddma", "dd")      # methods whose ``symbols`` are searched by det_symbol
+
+
+def unique_alphabet(symbols, method):
+    """For the methods that search their alphabet (``det_symbol``, pythran_equalisation.py:240-265): drop repeated
+    points of every row, keeping first occurrences in order.  ``det_symbol`` returns the VALUE of the first strict
+    minimum, and a repeat of an earlier point can never be a strict improvement, so the decisions -- and with them
+    every output -- are unchanged; the search gets as short as the alphabet really is.  This matters where a whole
+    training sequence is passed as ``symbols`` of such a method: the pilot equaliser hands ``sbd`` its 1024-symbol
+    QPSK pilot sequence (pilotbased_receiver.py:530-541), i.e. 4 distinct points.  Rows keep a common length (short
+    rows are padded with their own first point, which never wins a strict comparison against itself)."""
+    if method not in SEARCHED_ALPHABET:
+        return symbols
+    symbols = np.atleast_2d(symbols)
+    rows = []
+    for r in symbols:
+        _, first = np.unique(r, return_index=True)
+        rows.append(r[np.sort(first)])
+    K = max(len(r) for r in rows)
+    if K == symbols.shape[1]:
+        return symbols
+    return np.stack([np.concatenate([r, np.repeat(r[:1], K - len(r))]) for r in rows])
+
+
 def reshape_symbols(symbols, method, M, dtype, nmodes):
     """Bring user symbols to (nmodes, K) (equalisation.py:568-594).  For the real-valued methods
     ``nmodes`` counts the real rows (2 per polarisation) and ``dtype`` is the real dtype."""

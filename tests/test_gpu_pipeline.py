@@ -322,3 +322,28 @@ def test_dev_entry_points_are_cuda_graph_capturable(env):
     t.cuda.synchronize()
     assert t.equal(got[0], keep["out"]) and t.equal(got[1], keep["ph"]) and t.equal(got[2], w)
     assert not t.equal(got[0], ref1[0])
+
+
+def test_searched_alphabet_with_repeats_trains_like_its_unique_points(env):
+    """sbd with a whole QPSK training sequence as ``symbols`` (what the pilot equaliser passes,
+    pilotbased_receiver.py:530-541): the kernels searching all 512 entries and the host-side reduction to the 4
+    distinct points (theory.unique_alphabet) give bit-identical taps and errors."""
+    t = env.torch
+    rng = np.random.default_rng(5)
+    E, _ = env.synth.synth_numpy(4, 3000, seed=31, snr_db=22.0)
+    q = env.theory.normalised_symbols(4).astype(np.complex64)
+    seq = np.stack([q[rng.integers(0, 4, 512)], q[rng.integers(0, 4, 512)]])
+    uniq = env.theory.unique_alphabet(seq, "sbd")
+    assert uniq.shape == (2, 4)
+    Ed = t.from_numpy(E).to(env.dev)[None]
+    res = []
+    for sy in (seq, uniq):
+        for adaptive in (False, True):
+            w = t.from_numpy(env.theory.init_taps(17, 2, np.complex64)[None]).to(env.dev)
+            mu = t.full((1, 2), 2e-3, dtype=t.float32, device=env.dev)
+            err = t.zeros((1, 2, 2900), dtype=t.complex64, device=env.dev)
+            env.device.train_equaliser(Ed, 2900, 1, 2, mu, w, None, adaptive, t.from_numpy(np.ascontiguousarray(sy)).to(env.dev),
+                                       "sbd", err)
+            res.append((w.cpu().numpy(), err.cpu().numpy(), mu.cpu().numpy()))
+    for a, b in ((res[0], res[2]), (res[1], res[3])):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])

@@ -157,3 +157,33 @@ def test_synth_capture_is_blockwise_synth_signal():
         assert torch.equal(E[:, 2 * a:2 * (a + n)], Eb)
         if b == 0:
             assert torch.equal(s0, sb)
+
+
+def test_unique_alphabet_keeps_first_occurrences_and_decisions():
+    """A searched alphabet (sbd / mddma / dd) without its repeats gives the same det_symbol decisions
+    (pythran_equalisation.py:240-265: first STRICT minimum, the value is returned); other methods are untouched."""
+    from qampy_b200 import theory
+    rng = np.random.default_rng(3)
+    q = theory.normalised_symbols(4).astype(np.complex64)
+    seq = np.stack([q[rng.integers(0, 4, 1024)], q[rng.integers(0, 2, 1024)]])      # row 1 uses 2 points only
+    u = theory.unique_alphabet(seq, "sbd")
+    assert u.shape == (2, 4)
+    for r in range(2):
+        _, first = np.unique(seq[r], return_index=True)
+        k = first.size
+        assert np.array_equal(u[r, :k], seq[r][np.sort(first)]) and np.all(u[r, k:] == u[r, 0])
+
+    def det(x, sy):
+        d0, s = 1000., 1 + 0j
+        for v in sy:
+            d = abs(x - v) ** 2
+            if d < d0:
+                d0, s = d, v
+        return s
+    for _ in range(300):
+        x = complex(rng.normal(), rng.normal())
+        for r in range(2):
+            assert det(x, seq[r]) == det(x, u[r])
+    assert theory.unique_alphabet(seq, "sbd_data") is seq and theory.unique_alphabet(seq, "mcma") is seq
+    a16 = np.tile(theory.normalised_symbols(16).astype(np.complex64), (2, 1))
+    assert theory.unique_alphabet(a16, "dd") is a16
