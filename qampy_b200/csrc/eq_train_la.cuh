@@ -433,6 +433,10 @@ static int launch_la_method(const TrainParams<float> &p, const FastGeom &g, size
         return launch_la_pad<LPS, NQ, QB_CMA>(p, g, smem, st);
     case QB_MCMA:
         return launch_la_pad<LPS, NQ, QB_MCMA>(p, g, smem, st);
+    case QB_SBD:
+        return launch_la_pad<LPS, NQ, QB_SBD>(p, g, smem, st);
+    case QB_DD:
+        return launch_la_pad<LPS, NQ, QB_DD>(p, g, smem, st);
     case QB_RDE:
         if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC>(p, g, smem, st);
         if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_RDE3>(p, g, smem, st);

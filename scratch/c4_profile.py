@@ -18,3 +18,15 @@ pr = cProfile.Profile(); pr.enable()
 res = pilots.pilot_receiver(Ed, seq, php[:, :idx.size], idx_pil, fl, 2, frames, to_host=False)
 torch.cuda.synchronize(); pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(28)
+# per-call timing of the batched trainings
+import qampy_b200.equalisation as be
+orig = be.equalise_windows
+def timed(E, starts, window, os, mu, M, **kw):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = orig(E, starts, window, os, mu, M, **kw)
+    torch.cuda.synchronize()
+    print('equalise_windows nwin %3d window %5d method %-4s Niter %2d adaptive %s symbols %s modes %s: %.1f ms' % (
+        np.size(starts), window, kw.get('method'), kw.get('Niter', 1), kw.get('adaptive_stepsize'), 'yes' if kw.get('symbols') is not None else 'no', kw.get('modes'), 1e3 * (time.perf_counter() - t0)))
+    return r
+be.equalise_windows = timed
+res = pilots.pilot_receiver(Ed, seq, php[:, :idx.size], idx_pil, fl, 2, frames, to_host=False)
