@@ -5,6 +5,8 @@
 
 namespace qb {
 
+constexpr int GRID_MAX_K = 256;   // largest alphabet the grid slicer of the fast kernels handles (one byte per point)
+
 template <typename T>
 struct TrainParams {
     const cx<T> *E;
@@ -17,6 +19,7 @@ struct TrainParams {
     int nmodes, nsel, os, ntaps;
     int Niter, adaptive, method, K;
     int tile_syms, tile_pitch, nsym_smem;
+    int nsym_pitch;      // fast kernels: float2 slots per lane group (constants + scratch of the grid slicer)
     long long L;         // samples per row that may be read (fast kernel: bounds of the padded window)
     long long nstreams;  // nseg * nsel
     ModeList modes;

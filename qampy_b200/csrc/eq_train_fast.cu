@@ -32,6 +32,10 @@ int train_fast_try(TrainParams<float> p, cudaStream_t st)
     if (p.os != 2) return 0;
     if (!(p.nmodes == 1 || p.nmodes == 2 || p.nmodes == 4 || p.nmodes == 8)) return 0;
     p.nsym_smem = (p.method == QB_SBD_DATA) ? 0 : p.K;
+    // methods that search their alphabet get scratch for the grid slicer behind the staged constants
+    // (eq_train_fast.cuh, detect_grid): 32 axis levels + one byte per alphabet point
+    const bool searched = p.method == QB_SBD || p.method == QB_DD || p.method == QB_MDDMA;
+    p.nsym_pitch = p.nsym_smem + ((searched && p.K >= 4 && p.K <= GRID_MAX_K) ? 16 + (p.K + 7) / 8 : 0);
     // QB_TRAIN_LPS = 8 | 16 forces a layout (tests, tuning)
     int forced = 0;
     if (const char *e = getenv("QB_TRAIN_LPS")) forced = atoi(e);

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     float2 *syms = gsum + shared_len;                       // [GPW][nsym_smem]
 
     const float2 *gsyms = p.symbols + (long long)mode * p.K;
-    float2 *mysyms = syms + grp * p.nsym_smem;
+    float2 *mysyms = syms + grp * p.nsym_pitch;
     for (int c = gl; c < p.nsym_smem; c += LPS) mysyms[c] = gsyms[c];
 
     const int k = gl / g.lpp, t0 = (gl % g.lpp) * NQ;
@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     const float mu = p.mu[stream];
     const uint32_t errs_addr = smem_u32(errs + grp * g.tile_syms);
     __syncwarp();
-    const ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);
+    ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);
+    if (p.nsym_pitch > p.nsym_smem)   // searched alphabet: is it a square grid? (uniform)
+        detect_grid<LPS>(ec, mysyms, p.nsym_smem, reinterpret_cast<float *>(mysyms + p.nsym_smem), gl);
 
     const long long ntiles_it = (p.TrSyms + g.tile_syms - 1) / g.tile_syms;
     const long long ntiles = ntiles_it * p.Niter;
@@ -385,7 +387,7 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     if (2 * g.tile_syms + g.lpp * nq + 2 > 32 * GRAM_CH) return 0;
     const size_t shared_len = std::max((size_t)g.nslots * gram_sum_len(g.tile_syms, p.ntaps), (size_t)GPW * g.tile_syms);
     smem = ((size_t)2 * g.nslots * p.nmodes * g.pitch + (size_t)g.nslots * g.tile_syms + shared_len +
-            (size_t)GPW * p.nsym_smem) * sizeof(float2);
+            (size_t)GPW * p.nsym_pitch) * sizeof(float2);
     if (smem > 56 * 1024) return 0;   // four warp slices per CTA must fit 227 kB
     return nq;
 }

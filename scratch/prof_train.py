@@ -9,7 +9,7 @@ nseg = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 E, _ = synth.synth_signal(M, nseg * S + 100, seed=1, device=dev)
 Ev = device.segment_view(E, nseg, S, 2, ntaps)
 tr = theory.cal_training_symbol_len(2, ntaps, Ev.shape[2])
-for method in ('mcma', 'mrde'):
+for method in (sys.argv[2].split(',') if len(sys.argv) > 2 else ('mcma', 'mrde')):
     sy = torch.from_numpy(theory.reshape_symbols(None, method, M, np.complex64, 2)).to(dev)
     w0 = torch.from_numpy(np.tile(theory.init_taps(ntaps, 2, np.complex64), (nseg, 1, 1, 1))).to(dev)
     mu = torch.full((nseg, 2), 1e-3, dtype=torch.float32, device=dev)

@@ -347,3 +347,41 @@ def test_searched_alphabet_with_repeats_trains_like_its_unique_points(env):
             res.append((w.cpu().numpy(), err.cpu().numpy(), mu.cpu().numpy()))
     for a, b in ((res[0], res[2]), (res[1], res[3])):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("alphabet", ["apsk16", "qam16_rotated", "qam16_repeat", "qam16_shuffled", "qam256"])
+def test_searched_alphabets_grid_slicer_and_list_search(env, alphabet):
+    """sbd / dd / mddma decide with a per-axis slicer when the alphabet is a full square grid (detected in the kernel
+    from the staged points, any order) and with the list search otherwise: a ring alphabet, a rotated grid and a
+    grid with one point repeated must take the list search, a shuffled grid and 256-QAM the slicer -- all against
+    the oracle's det_symbol (pythran_equalisation.py:240-265)."""
+    t = env.torch
+    rng = np.random.default_rng(11)
+    q16 = env.theory.normalised_symbols(16).astype(np.complex64)
+    M = 16
+    if alphabet == "apsk16":
+        sy = np.concatenate([0.5 * np.exp(2j * np.pi * np.arange(4) / 4 + 0.3j * 0), 1.2 * np.exp(2j * np.pi * np.arange(12) / 12)])
+    elif alphabet == "qam16_rotated":
+        sy = q16 * np.exp(0.2j)
+    elif alphabet == "qam16_repeat":
+        sy = q16.copy()
+        sy[5] = sy[4]
+    elif alphabet == "qam16_shuffled":
+        sy = q16[rng.permutation(16)]
+    else:
+        M = 256
+        sy = env.theory.normalised_symbols(256)
+    sy = np.tile(np.asarray(sy).astype(np.complex64), (2, 1))
+    E, _ = env.synth.synth_numpy(M, 2600, seed=41, snr_db=30.0)
+    ntaps, tr = 21, 2500
+    for method in ("sbd", "dd", "mddma"):
+        for layout in ("throughput", "latency"):
+            w = t.from_numpy(env.theory.init_taps(ntaps, 2, np.complex64)[None]).to(env.dev)
+            mu = t.full((1, 2), 1e-3, dtype=t.float32, device=env.dev)
+            err = t.zeros((1, 2, tr), dtype=t.complex64, device=env.dev)
+            env.device.train_equaliser(t.from_numpy(E).to(env.dev)[None], tr, 1, 2, mu, w, None, False,
+                                       t.from_numpy(sy).to(env.dev), method, err, layout=layout)
+            wr = env.theory.init_taps(ntaps, 2, np.complex64)[None]
+            er, wr, _ = env.co.train_segments(E[None], tr, 1, 2, 1e-3, wr, np.arange(2), False, sy, method, mu_shared=False)
+            assert rms(err.cpu().numpy() - er) < 1e-5 * max(1.0, rms(er)), (alphabet, method, layout)
+            assert np.max(np.abs(w.cpu().numpy() - wr)) < 2e-5, (alphabet, method, layout)
