@@ -1,7 +1,12 @@
-// Instantiations of the LPS = 8 lanes-per-stream training kernel (eq_train_fast.cuh).
+// LPS = 8 lanes-per-stream training kernel (eq_train_fast.cuh): geometry and dispatch to the translation units that
+// hold the instantiations (eq_train_fast_l8a/b/c.cu).
 #include "eq_train_fast.cuh"
 
 namespace qb {
+
+int train_fast_l8_nqa(int nq, const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st);
+int train_fast_l8_nqb(int nq, const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st);
+int train_fast_l8_nqc(int nq, const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st);
 
 // Returns 1 if launched, 0 if the shape does not fit this layout, < 0 on error.
 int train_fast_l8(TrainParams<float> p, cudaStream_t st)
@@ -12,12 +17,9 @@ int train_fast_l8(TrainParams<float> p, cudaStream_t st)
     if (!nq) return 0;
     int rc;
     switch (nq) {
-    case 2: rc = launch_sub_method<8, 2>(p, g, smem, st); break;
-    case 4: rc = launch_sub_method<8, 4>(p, g, smem, st); break;
-    case 6: rc = launch_sub_method<8, 6>(p, g, smem, st); break;
-    case 8: rc = launch_sub_method<8, 8>(p, g, smem, st); break;
-    case 12: rc = launch_sub_method<8, 12>(p, g, smem, st); break;
-    case 16: rc = launch_sub_method<8, 16>(p, g, smem, st); break;
+    case 2: case 4: case 6: rc = train_fast_l8_nqa(nq, p, g, smem, st); break;
+    case 8: case 12: rc = train_fast_l8_nqb(nq, p, g, smem, st); break;
+    case 16: rc = train_fast_l8_nqc(nq, p, g, smem, st); break;
     default: return 0;
     }
     return rc == QB_OK ? 1 : rc;
