@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--seg", type=int, default=-1,
                     help="output symbols per segment; -1 = smallest length >= 8192 that fills whole GPU waves "
                          "(pipeline.balanced_segment_symbols), 0 = one segment")
-    ap.add_argument("--chunks", type=int, default=8, help="host<->device overlap chunks of the e2e path")
+    ap.add_argument("--chunks", type=int, default=6, help="host<->device overlap chunks of the e2e path (the last one "
+                                                          "is cut into 1/2 + 1/4 + 1/4 unless --no-taper)")
     ap.add_argument("--ntaps", type=int, default=45)
     ap.add_argument("--M", type=int, default=64)
     ap.add_argument("--angles", type=int, default=64)
@@ -56,6 +57,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-taper", action="store_true", help="e2e path: do not cut the last chunk into 1/2 + 1/4 + 1/4")
     return ap.parse_args()
 
 
@@ -364,7 +366,7 @@ def run_b200(a, rank, local_rank, world):
         for it in range(2 + a.steps):
             barrier()
             t0 = time.perf_counter()
-            outs = pipeline.run_host(rx, Eh, outs[0], outs[1], nchunks=a.chunks, E_dev=Ed)[:2]
+            outs = pipeline.run_host(rx, Eh, outs[0], outs[1], nchunks=a.chunks, E_dev=Ed, taper=not a.no_taper)[:2]
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if it >= 2:

@@ -205,13 +205,22 @@ class SegmentedReceiver:
         return res
 
 
-def _host_chunks(groups, nchunks):
+def _host_chunks(groups, nchunks, taper=True):
     """Split the main group into ``nchunks`` runs of whole segments; the end-aligned extra segment (if
-    any) becomes the last chunk.  Yields (first_symbol, nsym, nseg, drop, seg_index0)."""
+    any) becomes the last chunk.  Yields (first_symbol, nsym, nseg, drop, seg_index0).
+
+    ``taper``: the last run is cut once more into 1/2 + 1/4 + 1/4 of its segments.  The wall time of the overlapped
+    path ends with (last H2D) -> chain of the last run (as deep as any: a segment is a serial recurrence) -> its
+    D2H, so the shorter the last run, the shorter the copy that nothing can hide."""
     first, nsym, nseg, drop = groups[0]
     nchunks = max(1, min(nchunks, nseg))
-    for c in range(nchunks):
-        lo, hi = shard_segments(nseg, c, nchunks)
+    bounds = [shard_segments(nseg, c, nchunks) for c in range(nchunks)]
+    if taper and nchunks > 1 and bounds[-1][1] - bounds[-1][0] >= 8:
+        lo, hi = bounds.pop()
+        n = hi - lo
+        cuts = [lo, lo + n // 2, lo + n // 2 + n // 4, hi]
+        bounds += [(cuts[i], cuts[i + 1]) for i in range(3)]
+    for lo, hi in bounds:
         if hi > lo:
             yield first + lo * nsym, nsym, hi - lo, 0, lo
     if len(groups) > 1:
@@ -219,7 +228,7 @@ def _host_chunks(groups, nchunks):
         yield f2, n2, k2, d2, nseg
 
 
-def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None):
+def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None, taper=True):
     """End-to-end form of :meth:`SegmentedReceiver.run` for a capture in (pinned) HOST memory.
 
     The capture is cut into ``nchunks`` runs of whole segments; the H2D copy of chunk c+1, the chain of
@@ -239,11 +248,11 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None):
         ph_host = torch.empty((nseg_total, nmodes, S), dtype=rx.rdtype, pin_memory=True)
     if E_dev is None:
         E_dev = torch.empty((nmodes, L), dtype=rx.tdtype, device=rx.dev)
-    if rx._streams is None or len(rx._streams["comp"]) < min(nchunks + 1, 17):
+    if rx._streams is None or len(rx._streams["comp"]) < min(nchunks + 3, 19):
         # one compute stream per chunk: the training kernel is latency bound, so the chains of different
         # chunks must run side by side rather than queue behind each other
         rx._streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
-                           comp=[torch.cuda.Stream() for _ in range(min(nchunks + 1, 17))])
+                           comp=[torch.cuda.Stream() for _ in range(min(nchunks + 3, 19))])
     st = rx._streams
     main = torch.cuda.current_stream()
     for s_ in [st["h2d"], st["d2h"]] + st["comp"]:
@@ -251,7 +260,7 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None):
     events, rx.events = rx.events, None
     keep = []
     copied_to = 0                                                   # samples [0, copied_to) are on the device
-    for ci, (first, nsym, nseg, drop, seg0) in enumerate(_host_chunks(groups, nchunks)):
+    for ci, (first, nsym, nseg, drop, seg0) in enumerate(_host_chunks(groups, nchunks, taper)):
         need = min(L, (first + nsym * nseg) * cfg.os + cfg.ntaps - 1)
         ev_in = torch.cuda.Event()
         with torch.cuda.stream(st["h2d"]):
