@@ -228,7 +228,7 @@ def _host_chunks(groups, nchunks, taper=True):
         yield f2, n2, k2, d2, nseg
 
 
-def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=8, E_dev=None, taper=True):
+def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, taper=True):
     """End-to-end form of :meth:`SegmentedReceiver.run` for a capture in (pinned) HOST memory.
 
     The capture is cut into ``nchunks`` runs of whole segments; the H2D copy of chunk c+1, the chain of
