@@ -256,9 +256,6 @@ def run_b200(a, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     _lib.require_device()
     if world > 1:
-        # the one stdout line of this script is the JSON line: keep NCCL's version banner out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -420,6 +417,13 @@ def resolve_segments(a):
 
 
 def main():
+    # The one stdout line of this script is the JSON line.  Native libraries write to file descriptor 1 directly
+    # (NCCL prints its version banner there when the first communicator comes up): hand fd 1 to stderr for the
+    # whole run and keep the original stdout for Python's own print().
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     a = resolve_segments(parse())
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
