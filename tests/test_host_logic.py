@@ -187,3 +187,24 @@ def test_unique_alphabet_keeps_first_occurrences_and_decisions():
     assert theory.unique_alphabet(seq, "sbd_data") is seq and theory.unique_alphabet(seq, "mcma") is seq
     a16 = np.tile(theory.normalised_symbols(16).astype(np.complex64), (2, 1))
     assert theory.unique_alphabet(a16, "dd") is a16
+
+
+def test_host_chunks_tile_the_segments_and_taper_the_last_run():
+    """The overlapped host path cuts the main group into runs of whole segments (last run tapered 1/2 + 1/4 + 1/4,
+    the end-aligned extra segment last): every segment exactly once, in order."""
+    from qampy_b200 import pipeline
+    for nseg, extra in ((1182, True), (1184, False), (5, True), (1, False), (40, False)):
+        groups = [(0, 100, nseg, 0)] + ([(nseg * 100 - 37, 100, 1, 63)] if extra else [])
+        for nchunks in (1, 3, 6, 8, 64):
+            for taper in (True, False):
+                runs = list(pipeline._host_chunks(groups, nchunks, taper))
+                main = runs[:-1] if extra else runs
+                assert [r[4] for r in main] == list(np.cumsum([0] + [r[2] for r in main])[:-1])
+                assert sum(r[2] for r in main) == nseg and all(r[2] > 0 and r[1] == 100 and r[3] == 0 for r in main)
+                assert all(r[0] == r[4] * 100 for r in main)
+                if extra:
+                    assert runs[-1] == (nseg * 100 - 37, 100, 1, 63, nseg)
+                if taper and nchunks > 1 and nseg // min(nchunks, nseg) >= 8:
+                    assert len(main) == min(nchunks, nseg) + 2 and main[-1][2] <= main[0][2] // 3 + 1
+                else:
+                    assert len(main) == min(nchunks, nseg)
