@@ -25,6 +25,7 @@
 // (update) and i+1 (dot); tiles are staged from one pair (2 samples) before the tile's first symbol.
 #pragma once
 #include <algorithm>
+#include <type_traits>
 
 #include "eq_train_fast.cuh"
 
@@ -205,6 +206,10 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     float crp = 0.f, cip = 0.f;     // c_{i-1} = mu * e_{i-1}: the update that is still to be applied
     float pqr = 0.f, pqi = 0.f;     // this lane's partial of Q_i = X_i . W_{i-1}
 
+    // The whole tile / symbol loop, generic in how a searched alphabet is decided (det_symbol_sel): for sbd / dd it
+    // is compiled twice and the (uniform) choice is made once, out here, so that the loop stays one basic block.
+    auto run = [&](auto grid_tag) {
+    constexpr int GRID = decltype(grid_tag)::value;
     if (ntiles > 0) load_tile(0, tile0);
     for (long long gt = 0; gt < ntiles; gt++) {
         float *cur = (gt & 1) ? tile1 : tile0;
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                     b2 = fma2(xi, PR[q], b2);
                 }
                 const long long i = i0 + il;
-                const float2 e = err_fast<METHOD, LPS>(p.method, make_float2(yr, yi), ec, mysyms, p.K, gsyms,
+                const float2 e = err_fast<METHOD, LPS, GRID>(p.method, make_float2(yr, yi), ec, mysyms, p.K, gsyms,
                                                   live ? i : 0, gl);
                 // every lane of the group stores the same value; symbols past n are never copied out
                 asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(errs_addr + 8u * il), "f"(e.x), "f"(e.y)
@@ -356,6 +361,13 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
             for (int c = gl; c < n; c += LPS) eg[c] = errs[grp * g.tile_syms + c];
         }
         __syncwarp();
+    }
+    };   // run
+    if constexpr (METHOD == QB_SBD || METHOD == QB_DD) {
+        if (ec.gn) run(std::integral_constant<int, 1>{});
+        else run(std::integral_constant<int, 0>{});
+    } else {
+        run(std::integral_constant<int, -1>{});
     }
     if (active) {
 #pragma unroll
