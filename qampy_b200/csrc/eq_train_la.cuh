@@ -25,7 +25,6 @@
 // (update) and i+1 (dot); tiles are staged from one pair (2 samples) before the tile's first symbol.
 #pragma once
 #include <algorithm>
-#include <type_traits>
 
 #include "eq_train_fast.cuh"
 
@@ -106,7 +105,11 @@ __device__ __forceinline__ void tile_gram(const float *tile, int nslots, int nmo
     }
 }
 
-template <int LPS, int NQ, int METHOD, int NMASK>
+// GRID (sbd / dd only): the decision of a searched alphabet is compiled in -- 1 grid slicer, 0 list search -- so that
+// no branch sits in the symbol loop.  Whether an alphabet is a grid is found out in the kernel (detect_grid), so
+// both instantiations are launched back to back and each one works on the streams whose alphabet is its kind (all
+// or none of them in practice; the other launch returns after its prologue).  -1: decided at run time.
+template <int LPS, int NQ, int METHOD, int NMASK, int GRID = -1>
 __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<float> p, FastGeom g, int warp_smem)
 {
     static_assert(NQ % 2 == 0, "NQ must be even (os = 2: the window moves by one pair per symbol)");
@@ -169,6 +172,12 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);
     if (p.nsym_pitch > p.nsym_smem)   // searched alphabet: is it a square grid? (uniform)
         detect_grid<LPS>(ec, mysyms, p.nsym_smem, reinterpret_cast<float *>(mysyms + p.nsym_smem), gl);
+    bool act = active;              // this launch records results for this lane's stream
+    if (GRID >= 0) {
+        const bool mine = (ec.gn != 0) == (GRID == 1);
+        if (!__any_sync(0xffffffffu, mine && active)) return;
+        act = active && mine;
+    }
 
     const long long ntiles_it = (p.TrSyms + g.tile_syms - 1) / g.tile_syms;
     const long long ntiles = ntiles_it * p.Niter;
@@ -206,10 +215,6 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     float crp = 0.f, cip = 0.f;     // c_{i-1} = mu * e_{i-1}: the update that is still to be applied
     float pqr = 0.f, pqi = 0.f;     // this lane's partial of Q_i = X_i . W_{i-1}
 
-    // The whole tile / symbol loop, generic in how a searched alphabet is decided (det_symbol_sel): for sbd / dd it
-    // is compiled twice and the (uniform) choice is made once, out here, so that the loop stays one basic block.
-    auto run = [&](auto grid_tag) {
-    constexpr int GRID = decltype(grid_tag)::value;
     if (ntiles > 0) load_tile(0, tile0);
     for (long long gt = 0; gt < ntiles; gt++) {
         float *cur = (gt & 1) ? tile1 : tile0;
@@ -356,20 +361,13 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
             crp = cip = 0.f;
         }
         __syncwarp();
-        if (p.err && active) {
+        if (p.err && act) {
             float2 *eg = p.err + ((long long)seg * p.nmodes + mode) * (p.TrSyms * p.Niter) + it * p.TrSyms + i0;
             for (int c = gl; c < n; c += LPS) eg[c] = errs[grp * g.tile_syms + c];
         }
         __syncwarp();
     }
-    };   // run
-    if constexpr (METHOD == QB_SBD || METHOD == QB_DD) {
-        if (ec.gn) run(std::integral_constant<int, 1>{});
-        else run(std::integral_constant<int, 0>{});
-    } else {
-        run(std::integral_constant<int, -1>{});
-    }
-    if (active) {
+    if (act) {
 #pragma unroll
         for (int q = 0; q < NP; q++) {
             const float2 wr = unpack2(PR[q]), wi = unpack2(PI[q]);
@@ -404,13 +402,13 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     return nq;
 }
 
-template <int LPS, int NQ, int METHOD, int NMASK>
-static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
+template <int LPS, int NQ, int METHOD, int NMASK, int GRID>
+static int launch_la_one(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
     constexpr int GPW = 32 / LPS;
     static bool attr_done = false;
     if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK>,
+        QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK, GRID>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
@@ -420,10 +418,24 @@ static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem
     // multi-warp CTAs (small launches) ask for more than half of an SM's shared memory so that ONE of them fits an
     // SM and concurrent launches spread over the machine (eq_train_fast.cuh, TRAIN_WPB)
     const size_t dyn = wpb > 1 ? std::max((size_t)wpb * wsm, (size_t)116 * 1024) : wsm;
-    train_la_kernel<LPS, NQ, METHOD, NMASK><<<(unsigned)((nblk + wpb - 1) / wpb), 32 * wpb, dyn, st>>>(p, g, (int)wsm);
+    train_la_kernel<LPS, NQ, METHOD, NMASK, GRID><<<(unsigned)((nblk + wpb - 1) / wpb), 32 * wpb, dyn, st>>>(p, g, (int)wsm);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
+}
+
+template <int LPS, int NQ, int METHOD, int NMASK>
+static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
+{
+    if constexpr (METHOD == QB_SBD || METHOD == QB_DD) {
+        if (p.nsym_pitch > p.nsym_smem) {    // grid scratch staged: one launch per decision kind (see the kernel)
+            const int rc = launch_la_one<LPS, NQ, METHOD, NMASK, 1>(p, g, smem, st);
+            if (rc != QB_OK) return rc;
+        }
+        return launch_la_one<LPS, NQ, METHOD, NMASK, 0>(p, g, smem, st);
+    } else {
+        return launch_la_one<LPS, NQ, METHOD, NMASK, -1>(p, g, smem, st);
+    }
 }
 
 template <int LPS, int NQ, int METHOD>
