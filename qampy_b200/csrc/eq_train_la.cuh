@@ -25,6 +25,7 @@
 // (update) and i+1 (dot); tiles are staged from one pair (2 samples) before the tile's first symbol.
 #pragma once
 #include <algorithm>
+#include <type_traits>
 
 #include "eq_train_fast.cuh"
 
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
         cp_async_commit();
     };
 
+    float fx_prev = 0.f;            // latency layout: largest lane partial of the previous tile (0: none yet)
     float crp = 0.f, cip = 0.f;     // c_{i-1} = mu * e_{i-1}: the update that is still to be applied
     float pqr = 0.f, pqi = 0.f;     // this lane's partial of Q_i = X_i . W_{i-1}
 
@@ -237,6 +239,12 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
         // staged pair j (samples 2j, 2j+1 of the staged row) lives in slot j % B; symbol il of the tile
         // has its window in pairs il+1 .. il+NP, symbol il-1 in pairs il .. il+NP-1, symbol il+1 in il+2 ..
         f32x2 XR[B], XI[B];
+        // One pass over the tile's symbols.  FIXED (latency layout only): the 32 lane partials of the tap dot are
+        // summed as integers by REDUX after scaling by `fx_scale`, a power of two chosen per tile (below); the
+        // pass records the largest partial it has seen in `tmax`.  !FIXED: shuffle all-reduce, any magnitude.
+        float tmax = 0.f;
+        auto tile_pass = [&](auto fixed_tag, const float fx_scale, const float fx_inv) {
+        constexpr bool FIXED = decltype(fixed_tag)::value;
 #pragma unroll
         for (int q = 0; q <= NP; q++) {
             asm volatile("ld.shared.b64 %0, [%1];" : "=l"(XR[q]) : "r"(xre + 8u * q));
@@ -271,12 +279,13 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                 // ---- 1. all-reduce of the partial Q_il, hops interleaved with W += c_{il-1} conj(X_{il-1}) ----
                 float qr = pqr, qi = pqi;
                 const float ncr = -crp;
-                if constexpr (LPS == 32) {
-                    // one stream per warp (latency layout): the 32 partials are summed as 8.24 fixed point by ONE
-                    // warp-wide integer reduction each (REDUX) instead of five shuffle hops -- exact integer sum,
-                    // so the result does not depend on the lane order; the tap update hides its latency
-                    const int sr = __reduce_add_sync(0xffffffffu, __float2int_rn(pqr * 16777216.f));
-                    const int si = __reduce_add_sync(0xffffffffu, __float2int_rn(pqi * 16777216.f));
+                if constexpr (FIXED) {
+                    // one stream per warp (latency layout): the 32 partials are summed as block-floating fixed point
+                    // by ONE warp-wide integer reduction each (REDUX) instead of five shuffle hops -- exact integer
+                    // sum, so the result does not depend on the lane order; the tap update hides its latency
+                    tmax = fmaxf(tmax, fmaxf(fabsf(pqr), fabsf(pqi)));
+                    const int sr = __reduce_add_sync(0xffffffffu, __float2int_rn(pqr * fx_scale));
+                    const int si = __reduce_add_sync(0xffffffffu, __float2int_rn(pqi * fx_scale));
 #pragma unroll
                     for (int q = 0; q < NP; q++) {
                         f32x2 xr = XR[(u + q) % B], xi = XI[(u + q) % B];
@@ -290,10 +299,11 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                         PI[q] = fma2_bcast(ncr, xi, PI[q]);
                     }
                     // Q + c G with the Gram term formed first: only one FMA follows the reduction
-                    qr = fmaf((float)sr, 1.f / 16777216.f, fmaf(-cip, Gi.y, crp * Gi.x));
-                    qi = fmaf((float)si, 1.f / 16777216.f, fmaf(cip, Gi.x, crp * Gi.y));
+                    qr = fmaf((float)sr, fx_inv, fmaf(-cip, Gi.y, crp * Gi.x));
+                    qi = fmaf((float)si, fx_inv, fmaf(cip, Gi.x, crp * Gi.y));
                 } else {
-                    constexpr int NHOP = LPS == 8 ? 3 : 4;
+                    constexpr int NHOP = LPS == 8 ? 3 : (LPS == 16 ? 4 : 5);
+                    if constexpr (LPS == 32) tmax = fmaxf(tmax, fmaxf(fabsf(pqr), fabsf(pqi)));
 #pragma unroll
                     for (int h = 0; h < NHOP; h++) {
                         const int m = LPS >> (h + 1);
@@ -316,8 +326,8 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                     }
                 }
                 // ---- 2. y = Q + c_{il-1} G -> error -> c_il, interleaved with the partial dot Q_{il+1} ---------
-                const float yr = LPS == 32 ? qr : fmaf(-cip, Gi.y, fmaf(crp, Gi.x, qr));
-                const float yi = LPS == 32 ? qi : fmaf(cip, Gi.x, fmaf(crp, Gi.y, qi));
+                const float yr = FIXED ? qr : fmaf(-cip, Gi.y, fmaf(crp, Gi.x, qr));
+                const float yi = FIXED ? qi : fmaf(cip, Gi.x, fmaf(crp, Gi.y, qi));
                 f32x2 a1 = 0ull, a2 = 0ull, b1 = 0ull, b2 = 0ull;
 #pragma unroll
                 for (int q = 0; q < NP; q++) {
@@ -340,6 +350,41 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                 pqr = sa.x + sa.y;
                 pqi = sb.x + sb.y;
             }
+        }
+        };   // tile_pass
+        if constexpr (LPS == 32) {
+            // Block-floating scale of the integer reduction.  The reference does not normalise its input
+            // (equalise_signal trains on whatever amplitude it is given), so the scale follows the data: the largest
+            // lane partial of the PREVIOUS tile is mapped to [2^22, 2^23), which leaves 8x room before 32 lanes could
+            // wrap an int32 and a quantum at least as fine as the fp32 rounding of the partials themselves.  The
+            // pass records what it really saw; if that broke the bound (an amplitude step of more than 8x inside one
+            // tile) the tile is redone from its saved start state with the shuffle reduction, as is the first tile
+            // of a launch and any tile after a zero / non-finite one.
+            const float prev = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fx_prev)));
+            const int ex = (int)(__float_as_uint(prev) >> 23);               // biased exponent of the previous maximum
+            const bool usable = ex >= 32 && ex <= 222;                        // finite, non-zero, scale representable
+            bool redo = !usable;
+            if (usable) {
+                const float fx_scale = __uint_as_float((uint32_t)(127 + 22 + 127 - ex) << 23);   // 2^(22 - floor(log2 prev))
+                const float fx_inv = __uint_as_float((uint32_t)(ex - 22) << 23);
+                f32x2 sPR[NP], sPI[NP];
+#pragma unroll
+                for (int q = 0; q < NP; q++) sPR[q] = PR[q], sPI[q] = PI[q];
+                const float scr = crp, sci = cip, spr = pqr, spi = pqi;
+                tile_pass(std::true_type{}, fx_scale, fx_inv);
+                const float seen = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(tmax)));
+                redo = !(seen * fx_scale < 67108864.f);                       // 2^26 per lane; NaN -> redo
+                if (redo) {
+#pragma unroll
+                    for (int q = 0; q < NP; q++) PR[q] = sPR[q], PI[q] = sPI[q];
+                    crp = scr, cip = sci, pqr = spr, pqi = spi;
+                    tmax = 0.f;
+                }
+            }
+            if (redo) tile_pass(std::false_type{}, 0.f, 0.f);
+            fx_prev = tmax;
+        } else {
+            tile_pass(std::false_type{}, 0.f, 0.f);
         }
         if (tl == ntiles_it - 1) {
             // end of a training iteration: apply the pending update c_{T-1} conj(X_{T-1}).  The loop ended

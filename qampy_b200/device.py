@@ -37,14 +37,16 @@ def _modes_arg(modes, nmodes):
     return modes, modes.ctypes.data_as(ctypes.c_void_p)
 
 
-def segment_view(E, nseg, seg_out_symbols, os, ntaps):
+def segment_view(E, nseg, seg_out_symbols, os, ntaps, step_symbols=None):
     """Overlapping time-segment view (no copy) of a capture ``E`` (nmodes, L): segment s covers the
     input samples that produce output symbols [s*seg_out_symbols, (s+1)*seg_out_symbols), i.e.
     ``seg_out_symbols*os + ntaps - 1`` samples starting at ``s*seg_out_symbols*os`` (SURVEY.md section 5,
-    from N = (L - ntaps + 1)//os).  Returns a (nseg, nmodes, L_seg) strided view."""
+    from N = (L - ntaps + 1)//os).  ``step_symbols`` (default: ``seg_out_symbols``): distance between the first output
+    symbols of neighbouring segments, smaller than their length when segments overlap (pipeline: phase-search halo).
+    Returns a (nseg, nmodes, L_seg) strided view."""
     nmodes, L = E.shape
     L_seg = seg_out_symbols * os + ntaps - 1
-    step = seg_out_symbols * os
+    step = (seg_out_symbols if step_symbols is None else step_symbols) * os
     if (nseg - 1) * step + L_seg > L:
         raise ValueError("capture too short for %d segments of %d symbols" % (nseg, seg_out_symbols))
     return E.as_strided((nseg, nmodes, L_seg), (step, E.stride(0), 1), E.storage_offset())

@@ -36,6 +36,12 @@ class ReceiverConfig:
     bps_N: int = 45
     seg_symbols: int = None     # output symbols per segment; None = one segment (reference semantics)
     want_err: bool = False      # keep the per-symbol training error (reference returns it; 16 B/symbol/pass)
+    bps_halo: int = 0           # symbols of equalised signal on either side of a segment that its phase search also
+    #                             sees (0 = none).  The reference's bps leaves the first and last N symbols of a call
+    #                             without an estimate (phaserecovery.py:150-155: idx 0 -> rotated by angles[0]), so
+    #                             back-to-back segments need bps_halo >= bps_N for a seamless capture.
+    acq_symbols: int = 1 << 18  # training symbols per stage of SegmentedReceiver.acquire (tap acquisition)
+    acq_layout: str = "latency"  # training-kernel layout of the (single-stream) acquisition
 
 
 def plan_segments(L, cfg):
@@ -44,17 +50,22 @@ def plan_segments(L, cfg):
     the main group holds the N//S back-to-back segments; if S does not divide N, a second group holds
     ONE more segment of the same length aligned to the END of the capture (it overlaps its
     predecessor; only its last N % S symbols -- everything after ``drop`` -- are kept when stitching).
-    All segments therefore have the same length and cost, and the extra one runs concurrently."""
+    All segments therefore have the same length and cost, and the extra one runs concurrently.
+    A single segment (seg_symbols None or not shorter than the capture) is the reference call on the whole capture
+    and has no halo."""
     N = (L - cfg.ntaps + 1) // cfg.os
     if N <= 0:
         raise ValueError("capture shorter than the filter")
     S = cfg.seg_symbols
-    if S is None or S >= N:
+    H = int(cfg.bps_halo)
+    if S is None or S >= N - 2 * H:
         return [(0, N, 1, 0)]
-    nfull, rem = divmod(N, S)
-    groups = [(0, S, nfull, 0)]
+    # with a halo the segments tile [H, N - H): the H symbols at either end of the capture have no neighbour to
+    # borrow from (the reference gives them no phase estimate either)
+    nfull, rem = divmod(N - 2 * H, S)
+    groups = [(H, S, nfull, 0)]
     if rem:
-        groups.append((N - S, S, 1, S - rem))
+        groups.append((N - H - S, S, 1, S - rem))
     return groups
 
 
@@ -100,19 +111,21 @@ def max_over_ranks(value, device=None):
     return float(t.item())
 
 
-def rank_capture_range(nsym_total, ntaps, os, seg_symbols, rank, world):
+def rank_capture_range(nsym_total, ntaps, os, seg_symbols, rank, world, halo=0):
     """Sample range [a, b) of a long capture that ``rank`` must hold to produce ITS contiguous block of
-    segments (whole segments, ntaps-1 samples of overlap with the next rank, no exchange), plus the
-    range of output symbols it owns.  SURVEY.md section 8e."""
+    segments (whole segments, ntaps-1 samples -- plus ``halo`` symbols on either side when the phase search borrows
+    from the neighbours, ReceiverConfig.bps_halo -- of overlap with the next rank, no exchange), plus the
+    range of output symbols it owns.  A rank that runs plan_segments on its range with the same halo produces exactly
+    its own symbols.  SURVEY.md section 8e."""
     L = nsym_total * os
     N = (L - ntaps + 1) // os
-    nseg = N // seg_symbols
+    nseg = (N - 2 * halo) // seg_symbols
     lo, hi = shard_segments(nseg, rank, world)
-    first_sym, last_sym = lo * seg_symbols, hi * seg_symbols
+    first_sym, last_sym = halo + lo * seg_symbols, halo + hi * seg_symbols
     if rank == world - 1:
-        last_sym = N                      # the last rank also takes the remainder (end-aligned extra segment)
-    a = first_sym * os
-    b = min(L, a + (last_sym - first_sym) * os + ntaps - 1) if last_sym > first_sym else a
+        last_sym = N - halo               # the last rank also takes the remainder (end-aligned extra segment)
+    a = (first_sym - halo) * os
+    b = min(L, a + (last_sym - first_sym + 2 * halo) * os + ntaps - 1) if last_sym > first_sym else a
     return a, b, first_sym, last_sym
 
 
@@ -166,19 +179,53 @@ class SegmentedReceiver:
                                    self.syms[stage], cfg.methods[stage], err)
             t and t.record()
             errs.append(err)
+        # the final taps of a segment filter its own samples plus the halo on either side (H = 0: the same view)
+        H = cfg.bps_halo if first >= cfg.bps_halo else 0
+        next_ = nsym + 2 * H
+        Ea = Ev if H == 0 else device.segment_view(E[:, (first - H) * cfg.os:], nseg, next_, cfg.os, cfg.ntaps,
+                                                    step_symbols=nsym)
         t = self._tic("apply")
-        eq = device.apply_filter_to_signal(Ev, cfg.os, w)              # (nseg, nmodes, nsym)
+        eq = device.apply_filter_to_signal(Ea, cfg.os, w)              # (nseg, nmodes, nsym + 2 H)
         t and t.record()
         bin_ = eq if between is None else between(eq)
         t = self._tic("bps")
-        out, ph, idx = device.bps(bin_.reshape(nseg * self.nmodes, nsym), self.bps_tables, cfg.bps_N,
+        out, ph, idx = device.bps(bin_.reshape(nseg * self.nmodes, next_), self.bps_tables, cfg.bps_N,
                                   want_idx=self.want_idx)
         t and t.record()
         if idx is None:
             idx = ph
-        shp = (nseg, self.nmodes, nsym)
-        return dict(eq=eq, out=out.reshape(shp), ph=ph.reshape(shp), idx=idx.reshape(shp), taps=w, err=errs,
-                    first=first, nsym=nsym, nseg=nseg, drop=drop)
+        shp = (nseg, self.nmodes, next_)
+        ext = dict(eq=eq, out=out.reshape(shp), ph=ph.reshape(shp), idx=idx.reshape(shp))
+        own = {k: v[:, :, H:H + nsym] for k, v in ext.items()}         # the segment's own symbols (views)
+        return dict(own, ext=ext, halo=H, taps=w, err=errs, first=first, nsym=nsym, nseg=nseg, drop=drop)
+
+    def acquire(self, E, nsym=None, wxy0=None):
+        """Tap acquisition on the head of a capture: the reference call ``dual_mode_equalisation(E, os, mu, M,
+        wxy=wxy0 or Ntaps=ntaps, TrSyms=(A, A), methods=cfg.methods, apply=False)``
+        (``core/equalisation/equalisation.py:400-466``; ``_lms_init`` :391-397 cuts the field to the first
+        ``(A-1)*os + ntaps`` samples) -- ONE stream per mode, as deep as A symbols per stage, so it runs in the
+        single-stream layout of the trainer.  Short cold-started segments do not converge (64-QAM, mu 1e-3: SER
+        3e-4 after 8454 symbols, 0 after 2^18; scratch/conv_study.py); the taps acquired here are what every
+        segment of :meth:`run` starts from (``wxy0``), and what a streaming receiver carries from capture to
+        capture.  Returns taps (nmodes, nmodes, ntaps)."""
+        cfg = self.cfg
+        assert E.is_cuda and E.dim() == 2 and E.shape[0] == self.nmodes and E.stride(1) == 1
+        N = (E.shape[1] - cfg.ntaps + 1) // cfg.os
+        A = min(int(nsym or cfg.acq_symbols), N)
+        Ev = E[:, :(A - 1) * cfg.os + cfg.ntaps].unsqueeze(0)
+        w = (self.w0 if wxy0 is None else wxy0).clone().unsqueeze(0).contiguous()
+        for stage in range(len(cfg.methods)):
+            mu = torch.full((1, self.nmodes), float(cfg.mu[stage]), dtype=self.rdtype, device=self.dev)
+            t = self._tic("acquire")
+            device.train_equaliser(Ev, A, cfg.niter[stage], cfg.os, mu, w, None, False, self.syms[stage],
+                                   cfg.methods[stage], None, layout=cfg.acq_layout)
+            t and t.record()
+        return w[0]
+
+    @staticmethod
+    def carry_taps(res):
+        """Taps a streaming receiver hands to the next capture: those of the chronologically last full segment."""
+        return res[0]["taps"][-1]
 
     def run(self, E, wxy0=None, between=None):
         """E: (nmodes, L) complex CUDA tensor.  Returns one result dict per segment group (see
@@ -196,7 +243,7 @@ class SegmentedReceiver:
                 events, self.events = self.events, None      # per-launch events only on the main stream
                 res[1] = self._run_group(E, *groups[1], wxy0, between)
                 self.events = events
-                for v in res[1].values():
+                for v in list(res[1].values()) + list(res[1]["ext"].values()):
                     if torch.is_tensor(v):
                         v.record_stream(main)
         res[0] = self._run_group(E, *groups[0], wxy0, between)
@@ -228,26 +275,35 @@ def _host_chunks(groups, nchunks, taper=True):
         yield f2, n2, k2, d2, nseg
 
 
-def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, taper=True):
+def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, taper=True, wxy0=None, err_host=None):
     """End-to-end form of :meth:`SegmentedReceiver.run` for a capture in (pinned) HOST memory.
 
     The capture is cut into ``nchunks`` runs of whole segments; the H2D copy of chunk c+1, the chain of
     chunk c (on its own stream) and the D2H copy of the recovered symbols + phases of chunk c-1 overlap,
     so the wall time approaches max(copy in, compute, copy out) instead of their sum.  Results land in
-    ``out_host`` / ``ph_host`` with shape (nseg_total, nmodes, S) (segment major, like the device
-    layout; the last row is the end-aligned extra segment when S does not divide the capture).
-    Returns (out_host, ph_host, groups)."""
+    ``out_host`` / ``ph_host`` with shape (nseg_total, nmodes, S + 2*bps_halo) (segment major, like the device
+    layout; with a halo a segment's own symbols are columns [halo, halo + S); the last row is the end-aligned extra segment when S does not divide the capture).  With
+    ``cfg.want_err`` the per-symbol training errors of every stage (what the reference returns as ``(err1, err2)``,
+    ``equalisation.py:462-464``) are downloaded as well, into ``err_host`` = one pinned
+    (nseg_total, nmodes, TrSyms*Niter) array per stage.  ``wxy0``: the taps every segment starts from.
+    Returns (out_host, ph_host, groups) and, with ``cfg.want_err``, leaves the arrays in ``rx.err_host``."""
     cfg = rx.cfg
     nmodes, L = E_host.shape
     groups = plan_segments(L, cfg)
     nseg_total = sum(g[2] for g in groups)
     S = groups[0][1]
+    H = cfg.bps_halo if groups[0][0] >= cfg.bps_halo else 0     # rows hold the halo too: own symbols are [H, H + S)
     if out_host is None:
-        out_host = torch.empty((nseg_total, nmodes, S), dtype=rx.tdtype, pin_memory=True)
+        out_host = torch.empty((nseg_total, nmodes, S + 2 * H), dtype=rx.tdtype, pin_memory=True)
     if ph_host is None:
-        ph_host = torch.empty((nseg_total, nmodes, S), dtype=rx.rdtype, pin_memory=True)
+        ph_host = torch.empty((nseg_total, nmodes, S + 2 * H), dtype=rx.rdtype, pin_memory=True)
     if E_dev is None:
         E_dev = torch.empty((nmodes, L), dtype=rx.tdtype, device=rx.dev)
+    if cfg.want_err and err_host is None:
+        tr = theory.cal_training_symbol_len(cfg.os, cfg.ntaps, S * cfg.os + cfg.ntaps - 1)
+        err_host = [torch.empty((nseg_total, nmodes, tr * cfg.niter[k]), dtype=rx.tdtype, pin_memory=True)
+                    for k in range(len(cfg.methods))]
+    rx.err_host = err_host if cfg.want_err else None
     if rx._streams is None or len(rx._streams["comp"]) < min(nchunks + 3, 19):
         # one compute stream per chunk: the training kernel is latency bound, so the chains of different
         # chunks must run side by side rather than queue behind each other
@@ -261,7 +317,7 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, tap
     keep = []
     copied_to = 0                                                   # samples [0, copied_to) are on the device
     for ci, (first, nsym, nseg, drop, seg0) in enumerate(_host_chunks(groups, nchunks, taper)):
-        need = min(L, (first + nsym * nseg) * cfg.os + cfg.ntaps - 1)
+        need = min(L, (first + nsym * nseg + H) * cfg.os + cfg.ntaps - 1)
         ev_in = torch.cuda.Event()
         with torch.cuda.stream(st["h2d"]):
             if need > copied_to:
@@ -273,13 +329,18 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, tap
         ev_out = torch.cuda.Event()
         with torch.cuda.stream(comp):
             comp.wait_event(ev_in)
-            res = rx._run_group(E_dev, first, nsym, nseg, drop, None, None)
+            res = rx._run_group(E_dev, first, nsym, nseg, drop, wxy0, None)
             ev_out.record()
         with torch.cuda.stream(st["d2h"]):
             st["d2h"].wait_event(ev_out)
-            out_host[seg0:seg0 + nseg].copy_(res["out"], non_blocking=True)
-            ph_host[seg0:seg0 + nseg].copy_(res["ph"], non_blocking=True)
+            out_host[seg0:seg0 + nseg].copy_(res["ext"]["out"], non_blocking=True)
+            ph_host[seg0:seg0 + nseg].copy_(res["ext"]["ph"], non_blocking=True)
+            if cfg.want_err:
+                for k, e in enumerate(res["err"]):
+                    err_host[k][seg0:seg0 + nseg].copy_(e, non_blocking=True)
         keep.append(res)
+        if drop == 0:
+            rx.host_carry = res["taps"][-1]                         # taps of the last full segment (carry_taps)
     for s_ in [st["h2d"], st["d2h"]] + st["comp"]:
         main.wait_stream(s_)
     rx.events = events

@@ -188,3 +188,58 @@ def ser(E, syms, M, max_delay=64, probe=2000):
         m = min(dec.shape[1], ref.size - d)
         total.append(float(np.mean(np.abs(dec[r, :m] - ref[d:d + m]) > 1e-3)))
     return float(np.mean(total))
+
+
+def _nearest_index(x, alphabet, chunk=1 << 18):
+    """Index of the nearest alphabet point for every element of the complex tensor ``x`` (any shape)."""
+    flat = x.reshape(-1)
+    out = torch.empty(flat.shape, dtype=torch.int16, device=x.device)
+    for a in range(0, flat.numel(), chunk):
+        c = flat[a:a + chunk]
+        d = (c.real[:, None] - alphabet.real[None, :]) ** 2 + (c.imag[:, None] - alphabet.imag[None, :]) ** 2
+        out[a:a + chunk] = torch.argmin(d, dim=1).to(torch.int16)
+    return out.reshape(x.shape)
+
+
+def ser_segments(out, syms, M, firsts, probe=512, max_delay=32, seg_chunk=128):
+    """Symbol errors of EVERY segment of a segmented receiver run, on the tensors' own device (torch ops; this is
+    the bench's sanity gate, not a product path).
+
+    ``out`` (nseg, nmodes, S): recovered 1-sps symbols; ``syms`` (nmodes, nsym): what was sent; ``firsts`` (nseg,):
+    index of each segment's first output symbol in the capture.  What a blind receiver leaves open -- which sent
+    row an output row carries, a multiple-of-pi/2 rotation, the equaliser's symbol delay -- is resolved PER (segment,
+    row) on its first ``probe`` symbols (candidates: every sent row x 4 rotations x delays [0, max_delay)) and then
+    held for the whole segment.  Returns (errors (nseg, nmodes) int64, compared (nseg, nmodes) int64)."""
+    dev = out.device
+    nseg, nmodes, S = out.shape
+    nsrc, nsym = syms.shape
+    alphabet = torch.from_numpy(normalised_symbols(M)).to(dev).to(torch.complex64)
+    sent = _nearest_index(syms.to(torch.complex64), alphabet).to(torch.int64)                 # (nsrc, nsym)
+    # perm[r][k]: index of alphabet[k] * i^r
+    perm = torch.stack([_nearest_index(alphabet * (1j ** r), alphabet).to(torch.int64) for r in range(4)])
+    firsts = torch.as_tensor(firsts, dtype=torch.int64, device=dev)
+    P = min(probe, S)
+    errors = torch.zeros((nseg, nmodes), dtype=torch.int64, device=dev)
+    compared = torch.zeros((nseg, nmodes), dtype=torch.int64, device=dev)
+    ar_p = torch.arange(P, device=dev)
+    ar_d = torch.arange(max_delay, device=dev)
+    ar_s = torch.arange(S, device=dev)
+    for a in range(0, nseg, seg_chunk):
+        o = out[a:a + seg_chunk]
+        n = o.shape[0]
+        dec = _nearest_index(o.to(torch.complex64), alphabet).to(torch.int64)               # (n, nmodes, S)
+        f = firsts[a:a + n]
+        pos = (f[:, None, None] + ar_d[None, :, None] + ar_p[None, None, :]).clamp_(max=nsym - 1)    # (n, D, P)
+        cand = perm[:, sent[:, pos]]                                                         # (4, nsrc, n, D, P)
+        mism = (cand[None] != dec[:, :, :P].permute(1, 0, 2)[:, None, None, :, None, :]).sum(-1)   # (nmodes,4,nsrc,n,D)
+        best = mism.permute(3, 0, 1, 2, 4).reshape(n, nmodes, -1).argmin(-1)                 # (n, nmodes)
+        rot = best // (nsrc * max_delay)
+        src = (best // max_delay) % nsrc
+        dly = best % max_delay
+        p_all = f[:, None, None] + dly[:, :, None] + ar_s[None, None, :]                    # (n, nmodes, S)
+        valid = p_all < nsym
+        ref = sent.reshape(-1)[(src[:, :, None] * nsym + p_all.clamp(max=nsym - 1)).reshape(-1)].reshape(n, nmodes, S)
+        ref = perm.reshape(-1)[(rot[:, :, None] * perm.shape[1] + ref).reshape(-1)].reshape(n, nmodes, S)
+        errors[a:a + n] = ((ref != dec) & valid).sum(-1)
+        compared[a:a + n] = valid.sum(-1)
+    return errors, compared

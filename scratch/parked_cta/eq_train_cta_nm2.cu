@@ -1,0 +1,9 @@
+// Instantiation of the one-stream-per-CTA training kernel (eq_train_cta.cuh) for 2 input polarisation(s); one
+// translation unit per value so that they compile side by side.
+#include "eq_train_cta.cuh"
+
+namespace qb {
+
+int train_cta_nm2(TrainParams<float> p, cudaStream_t st) { return train_cta_nm<2>(p, st); }
+
+}  // namespace qb

@@ -208,3 +208,68 @@ def test_host_chunks_tile_the_segments_and_taper_the_last_run():
                     assert len(main) == min(nchunks, nseg) + 2 and main[-1][2] <= main[0][2] // 3 + 1
                 else:
                     assert len(main) == min(nchunks, nseg)
+
+
+def test_plan_segments_with_a_phase_search_halo():
+    """bps_halo: the segments tile [H, N - H); every segment plus H symbols on either side stays inside the capture;
+    a single segment has no halo (reference call on the whole capture)."""
+    H, S, ntaps = 45, 8192, 45
+    cfg = pipeline.ReceiverConfig(ntaps=ntaps, os=2, seg_symbols=S, bps_halo=H)
+    for L in (2 * 10 ** 6, 2 * (3 * S + 2 * H) + ntaps - 1, 2 * 40000 + 7):
+        N = (L - ntaps + 1) // 2
+        groups = pipeline.plan_segments(L, cfg)
+        assert groups[0][0] == H and groups[0][1] == S and groups[0][2] == (N - 2 * H) // S
+        covered = groups[0][1] * groups[0][2]
+        for first, nsym, nseg, drop in groups:
+            assert first - H >= 0 and ((first + nseg * nsym + H) - 1) * 2 + ntaps <= L
+        if len(groups) > 1:
+            first, nsym, nseg, drop = groups[1]
+            assert nseg == 1 and first + nsym == N - H
+            covered += nsym - drop
+        assert covered == N - 2 * H
+    assert pipeline.plan_segments(2 * 5000, cfg) == [(0, (2 * 5000 - ntaps + 1) // 2, 1, 0)]
+
+
+def test_rank_capture_ranges_with_halo_reproduce_the_single_process_plan():
+    """Every rank plans ITS sample range with the same halo and produces exactly the symbols it owns; the ranks
+    together produce [H, N - H) once."""
+    ntaps, S, H, nsym = 21, 1024, 21, 9000
+    cfg = pipeline.ReceiverConfig(ntaps=ntaps, os=2, seg_symbols=S, bps_halo=H)
+    N = (nsym * 2 - ntaps + 1) // 2
+    for world in (1, 2, 3):
+        nxt = H
+        for rank in range(world):
+            a, b, s0, s1 = pipeline.rank_capture_range(nsym, ntaps, 2, S, rank, world, halo=H)
+            assert s0 == nxt and a == (s0 - H) * 2 and b <= nsym * 2
+            nxt = s1
+            got = []
+            for first, n, nseg, drop in pipeline.plan_segments(b - a, cfg):
+                for s in range(nseg):
+                    lo = a // 2 + first + s * n
+                    got += list(range(lo + (drop if nseg == 1 else 0), lo + n))
+            assert got == list(range(s0, s1))
+        assert nxt == N - H
+
+
+def test_ser_segments_counts_errors_and_resolves_row_rotation_delay():
+    """bench.py's sanity gate: per (segment, row) the sent row, the pi/2 rotation and the delay are found on a probe."""
+    import torch
+    from qampy_b200 import synth
+    rng = np.random.default_rng(3)
+    M, nsym, S, nseg = 64, 9000, 2000, 4
+    al = theory.normalised_symbols(M).astype(np.complex64)
+    syms = al[rng.integers(0, M, (2, nsym))]
+    firsts = 30 + np.arange(nseg) * S
+    out = np.empty((nseg, 2, S), np.complex64)
+    for s in range(nseg):
+        d = 7 + s
+        out[s, 0] = syms[s % 2, firsts[s] + d: firsts[s] + d + S] * (1j ** s)          # rows swapped, rotated, delayed
+        out[s, 1] = syms[1 - s % 2, firsts[s] + d: firsts[s] + d + S] * (1j ** (s + 1))
+    out += 0.01 * (rng.standard_normal(out.shape) + 1j * rng.standard_normal(out.shape)).astype(np.complex64)
+    out[2, 1, 700] += al[0] - al[63]                                                     # three certain symbol errors
+    out[2, 1, 701] += al[0] - al[63]
+    out[3, 0, 1999] += al[63] - al[0]
+    e, c = synth.ser_segments(torch.from_numpy(out), torch.from_numpy(syms), M, firsts, seg_chunk=3)
+    want = np.zeros((nseg, 2), np.int64)
+    want[2, 1], want[3, 0] = 2, 1
+    assert np.array_equal(e.numpy(), want) and int(c.min()) == S
