@@ -336,9 +336,12 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
                 }
                 const unsigned vm = __ballot_sync(FULL, valid);
                 if (vm) p4prev = __shfl_sync(FULL, p4, 31 - __clz(vm));
-                if (NW > 1 && lane == 0) {
-                    ust[0] = cum;
-                    ust[1] = p4prev;
+                if (NW > 1) {
+                    __syncwarp();   // every lane has read the carried state before lane 0 replaces it
+                    if (lane == 0) {
+                        ust[0] = cum;
+                        ust[1] = p4prev;
+                    }
                 }
             }
         }

@@ -36,124 +36,10 @@ def _backend(backend):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# small host-side helpers
+# estimators (spectral frequency offset, sequence location, pilot phase / frequency): pilot_estimators.py
 # ---------------------------------------------------------------------------------------------------------
-def find_freq_offset(sig, os=1, average_over_modes=True, fft_size=2 ** 16):
-    """Frequency offset from the peak of the spectrum of sig**4 (phaserecovery.py:385-436)."""
-    if not ((np.log2(fft_size) % 2 == 0) | (np.log2(fft_size) % 2 == 1)):
-        fft_size = 2 ** (int(np.ceil(np.log2(fft_size))))
-    sig = np.atleast_2d(sig)
-    npols = sig.shape[0]
-    spec = np.abs(np.fft.fft(sig ** 4, fft_size, axis=-1)) ** 2
-    freq_vector = np.fft.fftfreq(fft_size, 1 / os) / 4
-    freq_offset = freq_vector[np.argmax(np.abs(spec.astype(np.float64)), axis=-1)].reshape(npols, 1)
-    if average_over_modes:
-        freq_offset = np.mean(freq_offset) * np.ones(freq_offset.shape)
-    return freq_offset
-
-
-def comp_freq_offset(sig, freq_offset, os=1):
-    """Remove a frequency offset: sig * exp(-2j pi t f / os), t = 1 .. L (phaserecovery.py:438-473)."""
-    ndim = np.ndim(sig)
-    sig = np.atleast_2d(sig)
-    npols, L = sig.shape
-    t = np.arange(1, L + 1, dtype=float)
-    out = np.zeros((npols, L), dtype=sig.dtype)
-    for l in range(npols):
-        out[l] = sig[l] * np.exp(-1j * (2 * np.pi * t * freq_offset[l] / os))
-    return out.flatten() if ndim == 1 else out
-
-
-def find_sequence_offset(x, y, show_cc=False):
-    """Shift of y against x from the peak of their cross-correlation (ber_functions.py:33-72)."""
-    from scipy.signal import fftconvolve
-    X, Y = 1. * x, 1. * y
-    ac = fftconvolve(X, (Y.conj() if np.iscomplexobj(Y) else Y)[::-1], 'full')
-    idx = abs(ac).argmax() - (Y.shape[0] - 1)
-    return (idx, ac) if show_cc else idx
-
-
-def find_sequence_offset_complex(x, y):
-    """As find_sequence_offset, trying the four quarter-turn rotations of y (ber_functions.py:74-106).
-    Returns (offset, rotated y, quarter turns, correlation peak)."""
-    if not np.iscomplexobj(x) and not np.iscomplexobj(y):
-        idx, acm = find_sequence_offset(x, y, show_cc=True)
-        return idx, y, 0, acm
-    acm, ii, ix = 0., 0, 0
-    for i in range(4):
-        idx, ac = find_sequence_offset(x, y * 1.j ** i, show_cc=True)
-        act = ac.real.max()
-        if act > acm:
-            ii, ix, acm = i, idx, act
-    return ix, y * 1.j ** ii, ii, acm
-
-
-def moving_average(sig, N=3):
-    """Length-N moving average via a running sum in the signal's dtype (filter.py:215-237)."""
-    s2 = np.atleast_2d(sig)
-    ret = np.cumsum(np.insert(s2, 0, 0, axis=-1), dtype=sig.dtype, axis=-1)
-    out = (ret[:, N:] - ret[:, :-N]) / N
-    return out.flatten() if np.ndim(sig) == 1 else out
-
-
-def correct_shifts(shift_factors, ntaps, os):
-    """Frame offsets found with ntaps[0] taps, corrected for an equaliser of ntaps[1] taps (:436-443)."""
-    shift_factors = np.asarray(shift_factors)
-    if not ((ntaps[1] - ntaps[0]) % os == 0):
-        raise ValueError("Taps for search and convergence impropper configured")
-    shift_factors -= int((ntaps[1] - ntaps[0]) / 2)
-    return shift_factors
-
-
-# ---------------------------------------------------------------------------------------------------------
-# pilot-based estimators
-# ---------------------------------------------------------------------------------------------------------
-def pilot_based_foe(rec_symbs, pilot_symbs):
-    """Frequency offset from a straight-line fit to the unwrapped pilot phase (pilotbased_receiver.py:32-73).
-    Returns (mean offset, per-mode offsets (npols, 1), fit intercepts (npols, 1))."""
-    rec_symbs, pilot_symbs = np.atleast_2d(rec_symbs), np.atleast_2d(pilot_symbs)
-    npols = rec_symbs.shape[0]
-    cond, per_mode = np.zeros([npols, 1]), np.zeros([npols, 1])
-    for l in range(npols):
-        phase = np.unwrap(np.angle(pilot_symbs[l].conj() * rec_symbs[l]))
-        fit = np.polyfit(np.arange(0, len(phase)), phase, 1)
-        per_mode[l, 0] = fit[0] / (2 * np.pi)
-        cond[l, 0] = fit[1]
-    return np.mean(per_mode), per_mode, cond
-
-
-def pilot_based_cpe_new(signal, pilot_symbs, pilot_idx, frame_len, seq_len=None, num_average=1, use_pilot_ratio=1,
-                        max_num_blocks=None, nframes=1):
-    """Carrier phase from periodically inserted pilots: unwrapped pilot phase, moving average over
-    ``num_average`` pilots, linear interpolation to every symbol, de-rotation (pilotbased_receiver.py:258-327).
-    Returns (compensated signal, phase trace), both truncated to ``nframes * frame_len``."""
-    assert num_average > 1, "need to take average over at least 3"
-    if not (num_average % 2):
-        num_average += 1
-        warnings.warn("Number of averages should be odd, adding one average, num_average={}".format(num_average))
-    signal, pilot_symbs = np.atleast_2d(signal), np.atleast_2d(pilot_symbs)
-    idx_sel = pilot_idx[:max_num_blocks:use_pilot_ratio]
-    nlen = min(frame_len * nframes, signal.shape[-1])
-    idx_full = np.ravel(np.broadcast_to(idx_sel, (nframes, idx_sel.shape[-1])) + (np.arange(nframes) * frame_len)[:, None])
-    idx_full = idx_full[idx_full < nlen]
-    rec_pilots = signal[:, idx_full]
-    pilot_symbs = np.tile(pilot_symbs[:, ::use_pilot_ratio], nframes)[:, :rec_pilots.shape[-1]]
-    assert rec_pilots.shape == pilot_symbs.shape, \
-        "Inproper pilot configuration, the number of received pilots differs from reference ones"
-    assert pilot_symbs.shape[-1] >= num_average, \
-        "Inpropper pilot symbol configuration. Larger averaging block size than total number of pilot symbols"
-    res_phase = np.unwrap(np.angle(pilot_symbs.conjugate() * rec_pilots), axis=-1)
-    res_phase_avg = moving_average(res_phase, num_average)
-    half = int((num_average - 1) / 2)
-    idx_avg = idx_full[half:-half]
-    assert idx_avg.shape[-1] == res_phase_avg.shape[-1], "averaged phase and new indices are not the same shape"
-    nmodes = pilot_symbs.shape[0]
-    trace = np.zeros((nmodes, nlen), dtype=pilot_symbs.dtype)        # the reference keeps the pilots' dtype here
-    grid = np.arange(0, nlen)
-    for i in range(nmodes):
-        trace[i] = np.interp(grid, idx_avg, res_phase_avg[i])
-    out = signal[:, :nlen] * np.exp(-1j * trace)
-    return out[:, :nframes * frame_len], trace[:, :nframes * frame_len]
+from .pilot_estimators import (comp_freq_offset, correct_shifts, find_freq_offset, find_sequence_offset,  # noqa: E402,F401
+                               find_sequence_offset_complex, moving_average, pilot_based_cpe_new, pilot_based_foe)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -184,57 +70,53 @@ def frame_sync(rx_signal, ref_symbs, os, frame_len=2 ** 16, M_pilot=4, mu=1e-3, 
     Returns (shift_factor per mode, coarse frequency offset, mode_sync_order, taps of the last mode's
     window, sync_ok)."""
     be = _backend(backend)
-    sync_ok = True
     rx_signal, ref_symbs = np.atleast_2d(rx_signal), np.atleast_2d(ref_symbs)
-    seq_len = ref_symbs.shape[-1]
-    nmodes = rx_signal.shape[0]
-    assert rx_signal.shape[-1] >= (frame_len + 2 * seq_len) * os, "Signal must be at least as long as frame"
+    nmodes, seq_len = rx_signal.shape[0], ref_symbs.shape[-1]
+    if rx_signal.shape[-1] < (frame_len + 2 * seq_len) * os:
+        raise AssertionError("the capture must hold one frame plus two pilot-sequence lengths")
     method = eqargs.get("method")
-    if method is not None:
-        if method in theory.REAL_VALUED and np.iscomplexobj(rx_signal):
-            raise ValueError("Equaliser method is {}, but using a real-valued equaliser in frame sync is "
-                             "unsupported".format(method))
-        if method in theory.DATA_AIDED:
-            raise ValueError("Equaliser method is {}, but using a data-aided equaliser in frame sync is "
-                             "unsupported".format(method))
-    overlap = 2                                   # windows per pilot-sequence length
-    window = seq_len * os
-    step = window // overlap
-    num_steps = (frame_len * os) // step + 1      # one frame plus one extra step
-    first = overlap                               # the first window position is skipped
-    starts = np.arange(first, num_steps) * step
+    if method in theory.REAL_VALUED and np.iscomplexobj(rx_signal):
+        raise ValueError("frame search with the real-valued equaliser method %s is not supported" % method)
+    if method in theory.DATA_AIDED:
+        raise ValueError("frame search with the data-aided equaliser method %s is not supported" % method)
+    window, hop, starts = _search_windows(seq_len, frame_len, os)
     # rx_device: the same signal already on the GPU (saves the upload of the capture for the window training)
     taps, errs = _train_windows(be, rx_signal if rx_device is None else rx_device, starts, window, os, mu, M_pilot,
                                 Ntaps, eqargs)
-    sub_vars = np.ones((nmodes, num_steps)) * 1e2
-    sub_vars[:, first:] = np.var(errs, axis=-1).T
-    wxys = np.zeros((num_steps, nmodes, nmodes, Ntaps), dtype=rx_signal.dtype)
-    wxys[first:] = taps
-    min_range = np.argmin(sub_vars, axis=-1)
-    mode_sync_order = np.zeros(nmodes, dtype=int)
+    # a window full of pilots (constant-modulus QPSK) leaves the blind equaliser with the smallest error variance
+    quietest = np.argmin(np.var(errs, axis=-1), axis=0)            # (nmodes,): window index per received mode
     shift_factor = np.zeros(nmodes, dtype=int)
-    todo = np.arange(0, nmodes)
-    foe_coarse, wx1 = None, None
-    for l in range(nmodes):
-        i_min = min_range[l]
-        long_seq = rx_signal[:, i_min * step - window:i_min * step + window]
-        wx1 = wxys[i_min]
-        symbs = be.apply_filter(long_seq, os, wx1)
+    mode_sync_order = np.zeros(nmodes, dtype=int)
+    free = np.ones(ref_symbs.shape[0], dtype=bool)                 # transmitted modes not yet claimed
+    sync_ok, foe_coarse, wx1 = True, None, None
+    for mode in range(nmodes):
+        start, wx1 = int(starts[quietest[mode]]), taps[quietest[mode]]
+        # three half-windows around the quietest one, equalised with its taps
+        symbs = be.apply_filter(rx_signal[:, start - window:start + window], os, wx1)
         foe_coarse = find_freq_offset(symbs)
-        symbs = comp_freq_offset(symbs, foe_coarse)
-        peak = np.zeros(nmodes, dtype=np.float64)
-        delay = np.zeros(nmodes, dtype=np.int32)
-        for ref_pol in todo:
-            ix, _, _, ac = find_sequence_offset_complex(ref_symbs[ref_pol], symbs[l])
-            delay[ref_pol], peak[ref_pol] = -ix, ac
-        best = np.argmax(peak)
-        if peak[best] < FRAME_SYNC_THRS:
-            warnings.warn("Very low autocorrelation, likely the frame-sync failed")
+        row = comp_freq_offset(symbs, foe_coarse)[mode]
+        peak = np.zeros(ref_symbs.shape[0])
+        lag = np.zeros(ref_symbs.shape[0], dtype=np.int64)
+        for cand in np.nonzero(free)[0]:
+            lag[cand], _, _, peak[cand] = find_sequence_offset_complex(ref_symbs[cand], row)
+        sent = int(np.argmax(peak))
+        if peak[sent] < FRAME_SYNC_THRS:
+            warnings.warn("frame search: correlation peak %.0f below %d, the pilot sequence was probably not found"
+                          % (peak[sent], FRAME_SYNC_THRS))
             sync_ok = False
-        mode_sync_order[l] = best
-        todo = todo[todo != best]
-        shift_factor[l] = i_min * step + os * delay[best] - window
+        free[sent] = False
+        mode_sync_order[mode] = sent
+        shift_factor[mode] = start - window - os * lag[sent]
     return shift_factor, foe_coarse, mode_sync_order, wx1, sync_ok
+
+
+def _search_windows(seq_len, frame_len, os):
+    """Candidate windows of the frame search: each one pilot-sequence long (``window`` samples), half a window apart
+    (``hop``), from one window into the capture up to one hop past a frame -- so that every window has a full window
+    of signal on either side.  Returns (window, hop, start sample of every candidate)."""
+    window = seq_len * os
+    hop = window // 2
+    return window, hop, hop * np.arange(2, (frame_len * os) // hop + 1)
 
 
 def sync2frame(rx_signal, pilot_seq, os, frame_len, M_pilot=4, backend=None, **kwargs):

@@ -86,6 +86,32 @@ class OracleLib:
         assert rc == 0
         return 0
 
+    def qb_make_decision_host(self, code, E, n, symbols, M, det, dist, idx):
+        ct, rt = _CT[code]
+        self.calls.append("decide")
+        d, ds, ix = self.co.make_decision(_arr(E, (n,), ct), _arr(symbols, (M,), ct))
+        _arr(det, (n,), ct)[...] = d
+        _arr(dist, (n,), rt)[...] = ds
+        _arr(idx, (n,), np.int32)[...] = ix
+        return 0
+
+    def qb_estimate_snr_host(self, code, rx, tx, n, gray, M, out):
+        ct, _ = _CT[code]
+        self.calls.append("snr")
+        _arr(out, (3,), np.float64)[...] = self.co.estimate_snr(_arr(rx, (n,), ct), _arr(tx, (n,), ct),
+                                                               _arr(gray, (M,), ct))
+        return 0
+
+    def qb_soft_l_value_demapper_host(self, code, rx, n, num_bits, snr, bits_map, nb, half, minmax, out):
+        ct, _ = _CT[code]
+        self.calls.append("demap")
+        bm = _arr(bits_map, (nb, half, 2), ct)
+        o = _arr(out, (n, num_bits), np.float64)
+        for a in range(0, n, 32768):       # the oracle forms (chunk, M/2) distance tables
+            o[a:a + 32768] = self.co.soft_l_value_demapper(_arr(rx, (n,), ct)[a:a + 32768], num_bits, snr, bm,
+                                                            minmax=bool(minmax))
+        return 0
+
     def qb_select_angles_host(self, code, angles, p, A, idx, L, out):
         rt = np.float32 if code == 0 else np.float64
         self.calls.append("select")
