@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record (one 1e9-sample capture over the ranks)")
     ap.add_argument("--no-taper", action="store_true", help="e2e path: do not cut the last chunk into 1/2 + 1/4 + 1/4")
     return ap.parse_args()
 
@@ -334,6 +335,99 @@ def measured_traffic(kernel_key, a):
         return None
 
 
+def host_link_probe(dev, world, nbytes=256 << 20, reps=3):
+    """What the box's host side can move while every rank copies in BOTH directions at once (pinned memory, one copy
+    engine each way): the ceiling of any end-to-end number.  Returns aggregate GB/s over all ranks (H2D + D2H bytes
+    / slowest rank's time)."""
+    import torch
+    import torch.distributed as dist
+    src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for r in range(reps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_in.copy_(src, non_blocking=True)
+        with torch.cuda.stream(s2):
+            dst.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        if r > 0:
+            best = dt if best is None else min(best, dt)
+    return 2.0 * nbytes * world / best / 1e9
+
+
+def c5_record(a, rank, world, dev):
+    """BASELINE config 5 inside the default line: ONE capture of 1e9 samples (5e8 symbols per polarisation) cut into
+    contiguous per-rank ranges of whole segments -- strong scaling, no collective on the data path.  Same chain,
+    same recipe (--start) and same gate as the headline; timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from qampy_b200 import pipeline, synth
+    nsym = 5 * 10 ** 8 // world
+    cfg0 = pipeline.ReceiverConfig(M=a.M, ntaps=a.ntaps, os=2)
+    seg = pipeline.balanced_segment_symbols(2 * nsym, cfg0, target=8192)
+    cfg = pipeline.ReceiverConfig(M=a.M, ntaps=a.ntaps, os=2, mu=(1e-3, 1e-3), methods=("mcma", "mrde"),
+                                  bps_angles=a.angles, bps_N=a.bpsN, seg_symbols=seg, want_err=not a.no_err,
+                                  acq_symbols=a.acq, acq_layout=a.acq_layout, bps_halo=a.bpsN)
+    rx = pipeline.SegmentedReceiver(cfg, dev)
+    rx.want_idx = False
+    E, syms0 = synth.synth_capture(a.M, nsym, seed=7000 + 100 * rank, snr_db=28.0, device=dev)
+    taps = rx.acquire(E) if a.start != "cold" else None
+
+    def step(taps):
+        if a.start == "acquire":
+            taps = rx.acquire(E)
+        res = rx.run(E, wxy0=taps)
+        return res, (rx.carry_taps(res) if a.start == "stream" else taps)
+
+    res, taps = step(taps)
+    del res
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    nstep = 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nstep):
+        res, taps = step(taps)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / nstep
+    g = res[0]
+    firsts = g["first"] + torch.arange(g["nseg"], device=dev) * g["nsym"]
+    keep = firsts + g["nsym"] <= syms0.shape[1] - 64          # block 0 of the block-wise capture
+    e, c = synth.ser_segments(g["out"][keep], syms0, a.M, firsts[keep])
+    stats = torch.tensor([float(e.sum()), float(c.sum())], device=dev, dtype=torch.float64)
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    ser = float(stats[0] / stats[1].clamp(min=1))
+    L = E.shape[1]
+    del res, E
+    torch.cuda.empty_cache()
+    ok = ser < 1e-5
+    return {"workload": "C5: one capture of 1e9 samples (5e8 symbols per polarisation) over %d GPU(s), %d symbols per "
+                        "GPU in segments of %d; same chain, recipe and gate as the headline" % (world, nsym, seg),
+            "scaling": "strong", "value": (world * L / (ms * 1e-3) / 1e6) if ok else None, "unit": "Msamples/s",
+            "ms_per_step": ms, "steps": nstep, "n_gpus": world, "ser": ser,
+            "symbols_compared": int(stats[1].item())}
+
+
 def run_b200(a, rank, local_rank, world):
     import numpy as np
     import torch
@@ -546,6 +640,23 @@ def run_b200(a, rank, local_rank, world):
                "api": "pinned host capture -> qampy_b200.pipeline.run_host (H2D / chain / D2H overlapped per "
                       "chunk of segments) -> pinned host symbols + phase + training errors"}
 
+    link_gbs = None
+    if not a.no_e2e:
+        link_gbs = host_link_probe(dev, world)
+        if e2e is not None:
+            e2e["host_link"] = {"aggregate_gbs_both_directions": link_gbs,
+                                "floor_ms_per_step": (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) * world
+                                / (link_gbs * 1e9) * 1e3,
+                                "note": "all ranks copying pinned memory H2D and D2H at once (256 MB each way, slowest "
+                                        "rank): what the host side of this box moves, the ceiling of any e2e number"}
+    c5 = None
+    if a.workload == "c3" and not a.no_c5:
+        caps.clear()
+        torch.cuda.empty_cache()
+        try:
+            c5 = c5_record(a, rank, world, dev)
+        except Exception as exc:
+            c5 = {"error": repr(exc)}
     if rank == 0:
         ok = ser_all < 1e-5
         line = {"metric": METRIC, "value": value if ok else None, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps,
@@ -567,6 +678,8 @@ def run_b200(a, rank, local_rank, world):
                 "note": "dual_mode_equalisation(TrSyms=(A, A), apply=False) from centre-spike taps on the head of a "
                         "capture, one serial stream per mode; --start stream pays it once per link (before the "
                         "warm-up steps), --start acquire once per capture inside every timed step"}
+        if c5 is not None:
+            line["c5"] = c5
         if world == 1 and not a.no_cpu_baseline:
             try:
                 line["cpu_baseline"], _ = cpu_baseline(a, a.cpu_seconds)

@@ -190,6 +190,31 @@ int qb_pilot_cpe_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride
                      int64_t num_average, void *out, int64_t out_stride, void *trace, int64_t trace_stride,
                      void *stream);
 
+/* ---- signal synthesis on the device (device pointers only) ---------------------------------
+ * The spectral / element-wise stages of the reference's generators around cuFFT (the caller owns the FFTs):
+ *   qampy/core/resample.py:73-126 rrcos_resample (+ core/filter.py:177-212 rrcos_pulseshaping, fftconvolve "same"),
+ *   qampy/core/impairments.py:94-131 apply_PMD_to_field, :133-186 phase_noise / apply_phase_noise, :188-233 add_awgn /
+ *   change_snr.  All arrays complex128 (the reference generates in double) except the final output.
+ * qb_synth_upsample_dev   out[r, up*k] = symbols[r, k], zero elsewhere up to out_stride (the FFT length).
+ * qb_synth_specmul_dev    X[r, k] *= H[k]: spectrum of a row times the spectrum of the zero-padded tap vector.
+ * qb_synth_crop_norm_dev  out[r, t] = x[r, first + t*down], t < n ("same" crop of the convolution + decimation); with
+ *                         renormalise: centred and scaled to power target_power[r] (normalise_and_center * sqrt(p)).
+ * qb_synth_pmd_dev        spectra (2, n) in FFT order of the two polarisations: rotate(theta), axis delays
+ *                         exp(-+ i omega t_dgd / 2) with omega on the reference's grid, rotate(-theta); in place.
+ * qb_synth_tail_dev       out[r, t] = (x[r, t] + noise_sigma[r] (N + iN)/sqrt(2)) * exp(i phase[r, t]), phase = phase0[r]
+ *                         + running sum of N(0, walk_sigma^2) steps; deviates from a counter-based generator keyed by
+ *                         (seed, row0 + r, index0 + t) so that blocks of one capture can be made independently
+ *                         (index0 even); noise_sigma NULL / walk_sigma 0 switch a stage off; phase_out optional.   */
+int qb_synth_upsample_dev(const void *symbols, int64_t nrows, int64_t n, int64_t up, void *out, int64_t out_stride,
+                          void *stream);
+int qb_synth_specmul_dev(void *X, int64_t nrows, int64_t nfft, const void *H, void *stream);
+int qb_synth_crop_norm_dev(const void *x, int64_t nrows, int64_t row_stride, int64_t first, int64_t down, int64_t n,
+                           const double *target_power, int renormalise, void *out, void *stream);
+int qb_synth_pmd_dev(void *spectra, int64_t n, double theta, double t_dgd, double fs, void *stream);
+int qb_synth_tail_dev(int dtype, const void *x, int64_t nrows, int64_t n, const double *noise_sigma, double walk_sigma,
+                      uint64_t seed, int64_t row0, int64_t index0, const double *phase0, void *out, int64_t out_stride,
+                      double *phase_out, void *stream);
+
 /* ---- Viterbi-Viterbi M-th power phase recovery, qampy/core/phaserecovery.py:40-79 ---------------------
  * For every row r of E (nrows, L): ph[r, w] = (unwrap(angle(sum_{t=w..w+N-1} (E[r,t]/|E[r,t]|)^M)) - pi)/M for the
  * L-N+1 windows, out[r, o+w] = E[r, o+w]*exp(-1j*ph[r, w]) with o = (N-1)/2 and zeros where no full window

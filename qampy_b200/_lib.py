@@ -45,6 +45,12 @@ PROTOTYPES = {
     "qb_estimate_snr_host": ([_int, _vp, _vp, _i64, _vp, _i64, _vp], _int),
     "qb_viterbiviterbi_dev": ([_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp], _int),
     "qb_viterbiviterbi_host": ([_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp], _int),
+    "qb_synth_upsample_dev": ([_vp, _i64, _i64, _i64, _vp, _i64, _vp], _int),
+    "qb_synth_specmul_dev": ([_vp, _i64, _i64, _vp, _vp], _int),
+    "qb_synth_crop_norm_dev": ([_vp, _i64, _i64, _i64, _i64, _i64, _vp, _int, _vp, _vp], _int),
+    "qb_synth_pmd_dev": ([_vp, _i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp], _int),
+    "qb_synth_tail_dev": ([_int, _vp, _i64, _i64, _vp, ctypes.c_double, ctypes.c_uint64, _i64, _i64, _vp, _vp, _i64,
+                           _vp, _vp], _int),
     "qb_freq_shift_dev": ([_int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp], _int),
     "qb_pilot_cpe_dev": ([_int, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp], _int),
     "qb_select_angles_dev": ([_int, _vp, _i64, _i64, _vp, _i64, _vp, _vp], _int),

@@ -47,6 +47,14 @@ int pilot_cpe_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stri
                        const void *pilots, int64_t pilot_stride, int64_t nph, int64_t navg, void *out,
                        int64_t out_stride, void *trace, int64_t trace_stride, cudaStream_t st);
 
+int synth_upsample_dispatch(const void *sym, int64_t rows, int64_t n, int64_t up, void *out, int64_t out_stride, cudaStream_t st);
+int synth_specmul_dispatch(void *X, int64_t rows, int64_t nfft, const void *H, cudaStream_t st);
+int synth_crop_norm_dispatch(const void *x, int64_t rows, int64_t row_stride, int64_t first, int64_t down, int64_t n,
+                             const double *target_power, int renorm, double *mom, void *out, cudaStream_t st);
+int synth_pmd_dispatch(void *S, int64_t n, double theta, double t_dgd, double fs, cudaStream_t st);
+int synth_tail_dispatch(int dtype, const void *x, int64_t rows, int64_t n, const double *noise_sigma, double walk_sigma,
+                        uint64_t seed, int64_t row0, uint64_t index0, const double *phase0, double *tile_buf, void *out,
+                        int64_t out_stride, double *phase_out, cudaStream_t st);
 int vv_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, int64_t N, int64_t M, void *out,
                 int64_t out_stride, void *ph, int64_t ph_stride, void *work, cudaStream_t st);
 size_t vv_work_bytes(int dtype, int64_t nrows, int64_t L, int64_t N);
@@ -574,6 +582,58 @@ static int vv_check(int64_t nrows, int64_t L, int64_t N, int64_t M)
     QB_REQUIRE(N >= 1 && L >= N, "the averaging length N must be between 1 and the signal length");
     QB_REQUIRE(M >= 1 && M <= 1024, "PSK order M out of range");
     return QB_OK;
+}
+
+int qb_synth_upsample_dev(const void *symbols, int64_t nrows, int64_t n, int64_t up, void *out, int64_t out_stride,
+                          void *stream)
+{
+    QB_REQUIRE(nrows >= 0 && n >= 0 && up >= 1 && out_stride >= n * up, "invalid sizes");
+    QB_REQUIRE(nrows <= 65535, "at most 65535 rows");
+    QB_REQUIRE(nrows == 0 || out_stride == 0 || (symbols && out), "symbols and out must not be NULL");
+    return synth_upsample_dispatch(symbols, nrows, n, up, out, out_stride, (cudaStream_t)stream);
+}
+
+int qb_synth_specmul_dev(void *X, int64_t nrows, int64_t nfft, const void *H, void *stream)
+{
+    QB_REQUIRE(nrows >= 0 && nrows <= 65535 && nfft >= 0, "invalid sizes");
+    QB_REQUIRE(nrows == 0 || nfft == 0 || (X && H), "X and H must not be NULL");
+    return synth_specmul_dispatch(X, nrows, nfft, H, (cudaStream_t)stream);
+}
+
+int qb_synth_crop_norm_dev(const void *x, int64_t nrows, int64_t row_stride, int64_t first, int64_t down, int64_t n,
+                           const double *target_power, int renormalise, void *out, void *stream)
+{
+    QB_REQUIRE(nrows >= 0 && nrows <= 65535 && n >= 0 && first >= 0 && down >= 1, "invalid sizes");
+    QB_REQUIRE(n == 0 || first + (n - 1) * down < row_stride, "crop reaches past the row");
+    QB_REQUIRE(nrows == 0 || n == 0 || (x && out && (!renormalise || target_power)), "x, out (and target_power) must not be NULL");
+    if (nrows == 0 || n == 0) return QB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf mom(st);
+    QB_TRY(mom.alloc((size_t)nrows * 3 * sizeof(double)));
+    return synth_crop_norm_dispatch(x, nrows, row_stride, first, down, n, target_power, renormalise, (double *)mom.p, out, st);
+}
+
+int qb_synth_pmd_dev(void *spectra, int64_t n, double theta, double t_dgd, double fs, void *stream)
+{
+    QB_REQUIRE(n >= 0, "invalid sizes");
+    QB_REQUIRE(n == 0 || spectra, "spectra must not be NULL");
+    return synth_pmd_dispatch(spectra, n, theta, t_dgd, fs, (cudaStream_t)stream);
+}
+
+int qb_synth_tail_dev(int dtype, const void *x, int64_t nrows, int64_t n, const double *noise_sigma, double walk_sigma,
+                      uint64_t seed, int64_t row0, int64_t index0, const double *phase0, void *out, int64_t out_stride,
+                      double *phase_out, void *stream)
+{
+    QB_TRY(check_dtype(dtype));
+    QB_REQUIRE(nrows >= 0 && nrows <= 65535 && n >= 0 && out_stride >= n && row0 >= 0 && index0 >= 0, "invalid sizes");
+    QB_REQUIRE(index0 % 2 == 0, "index0 must be even (walk steps are drawn in pairs)");
+    QB_REQUIRE(nrows == 0 || n == 0 || (x && out), "x and out must not be NULL");
+    if (nrows == 0 || n == 0) return QB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf tiles(st);
+    QB_TRY(tiles.alloc((size_t)nrows * ((n + 2047) / 2048) * sizeof(double)));
+    return synth_tail_dispatch(dtype, x, nrows, n, noise_sigma, walk_sigma, seed, row0, (uint64_t)index0, phase0,
+                               (double *)tiles.p, out, out_stride, phase_out, st);
 }
 
 int qb_viterbiviterbi_dev(int dtype, const void *E, int64_t nrows, int64_t row_stride, int64_t L, int64_t N, int64_t M,

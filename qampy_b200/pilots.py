@@ -70,19 +70,29 @@ def frame_sync(rx_signal, ref_symbs, os, frame_len=2 ** 16, M_pilot=4, mu=1e-3, 
     Returns (shift_factor per mode, coarse frequency offset, mode_sync_order, taps of the last mode's
     window, sync_ok)."""
     be = _backend(backend)
-    rx_signal, ref_symbs = np.atleast_2d(rx_signal), np.atleast_2d(ref_symbs)
+    ref_symbs = np.atleast_2d(ref_symbs)
+    on_device = rx_device is not None
+    if on_device:
+        # the capture is resident on the GPU: the stretch around the quietest window is filtered, de-rotated and
+        # correlated there (own FIR / frequency-shift kernels, cuFFT); a handful of scalars come back
+        import torch
+        from . import device
+        rx_signal = rx_device
+        ref_dev = torch.from_numpy(np.ascontiguousarray(ref_symbs)).to(rx_device.device)
+        is_complex = rx_device.is_complex()
+    else:
+        rx_signal = np.atleast_2d(rx_signal)
+        is_complex = np.iscomplexobj(rx_signal)
     nmodes, seq_len = rx_signal.shape[0], ref_symbs.shape[-1]
     if rx_signal.shape[-1] < (frame_len + 2 * seq_len) * os:
         raise AssertionError("the capture must hold one frame plus two pilot-sequence lengths")
     method = eqargs.get("method")
-    if method in theory.REAL_VALUED and np.iscomplexobj(rx_signal):
+    if method in theory.REAL_VALUED and is_complex:
         raise ValueError("frame search with the real-valued equaliser method %s is not supported" % method)
     if method in theory.DATA_AIDED:
         raise ValueError("frame search with the data-aided equaliser method %s is not supported" % method)
     window, hop, starts = _search_windows(seq_len, frame_len, os)
-    # rx_device: the same signal already on the GPU (saves the upload of the capture for the window training)
-    taps, errs = _train_windows(be, rx_signal if rx_device is None else rx_device, starts, window, os, mu, M_pilot,
-                                Ntaps, eqargs)
+    taps, errs = _train_windows(be, rx_signal, starts, window, os, mu, M_pilot, Ntaps, eqargs)
     # a window full of pilots (constant-modulus QPSK) leaves the blind equaliser with the smallest error variance
     quietest = np.argmin(np.var(errs, axis=-1), axis=0)            # (nmodes,): window index per received mode
     shift_factor = np.zeros(nmodes, dtype=int)
@@ -91,14 +101,23 @@ def frame_sync(rx_signal, ref_symbs, os, frame_len=2 ** 16, M_pilot=4, mu=1e-3, 
     sync_ok, foe_coarse, wx1 = True, None, None
     for mode in range(nmodes):
         start, wx1 = int(starts[quietest[mode]]), taps[quietest[mode]]
-        # three half-windows around the quietest one, equalised with its taps
-        symbs = be.apply_filter(rx_signal[:, start - window:start + window], os, wx1)
-        foe_coarse = find_freq_offset(symbs)
-        row = comp_freq_offset(symbs, foe_coarse)[mode]
+        # three half-windows around the quietest one, equalised with its taps, coarse frequency offset removed
+        stretch = rx_signal[:, start - window:start + window]
+        if on_device:
+            wd = torch.from_numpy(np.ascontiguousarray(wx1)).to(rx_device.device)
+            symbs = device.apply_filter_to_signal(stretch.unsqueeze(0), os, wd.unsqueeze(0))[0]
+            foe_coarse = find_freq_offset(symbs)
+            row = device.freq_shift(symbs, foe_coarse[:, 0], 1)[mode]
+            refs = ref_dev
+        else:
+            symbs = be.apply_filter(stretch, os, wx1)
+            foe_coarse = find_freq_offset(symbs)
+            row = comp_freq_offset(symbs, foe_coarse)[mode]
+            refs = ref_symbs
         peak = np.zeros(ref_symbs.shape[0])
         lag = np.zeros(ref_symbs.shape[0], dtype=np.int64)
         for cand in np.nonzero(free)[0]:
-            lag[cand], _, _, peak[cand] = find_sequence_offset_complex(ref_symbs[cand], row)
+            lag[cand], _, _, peak[cand] = find_sequence_offset_complex(refs[cand], row)
         sent = int(np.argmax(peak))
         if peak[sent] < FRAME_SYNC_THRS:
             warnings.warn("frame search: correlation peak %.0f below %d, the pilot sequence was probably not found"
@@ -379,7 +398,8 @@ def pilot_receiver(rx_signal, pilot_seq, ph_pilots, idx_pil, frame_len, os, fram
     (``signals.py:1709-1747``, ``qampy/equalisation.py:336-397``, ``qampy/phaserec.py:156-192``).  One upload of
     the capture; the frame search, the frequency shift, the pilot trainings of all frames (frame 0 first, the
     others side by side from its taps), the FIRs and the per-frame phase recovery are CUDA launches on device
-    data; the host sees a 4k-sample stretch for the sequence correlation and the final result.
+    data -- including the frame search's spectral frequency-offset estimate and sequence correlation (cuFFT); the host
+    sees a few scalars and the final result.
 
     ``ph_pilots`` (nmodes, n_ph): the phase pilots of one frame; ``idx_pil`` (frame_len,) bool: pilot positions
     in a frame (the first ``pilot_seq.shape[-1]`` are the sequence).  Returns a dict: ``out`` (nmodes,
@@ -390,19 +410,15 @@ def pilot_receiver(rx_signal, pilot_seq, ph_pilots, idx_pil, frame_len, os, fram
     from ._lib import require_device
     require_device()
     dev = torch.device("cuda", torch.cuda.current_device())
-    rx_host = None if torch.is_tensor(rx_signal) else np.atleast_2d(np.asarray(rx_signal))
-    Ed = rx_signal.to(dev) if torch.is_tensor(rx_signal) else torch.from_numpy(np.ascontiguousarray(rx_host)).to(dev)
+    Ed = rx_signal.to(dev) if torch.is_tensor(rx_signal) else \
+        torch.from_numpy(np.ascontiguousarray(np.atleast_2d(np.asarray(rx_signal)))).to(dev)
     pilot_seq = np.atleast_2d(pilot_seq)
     sl = pilot_seq.shape[-1]
-    if rx_host is None:
-        # capture already on the GPU: the frame search looks at one frame plus two window lengths and takes a
-        # 4k-sample stretch of it on the host -- download that much, not the capture
-        rx_host = Ed[:, :min(Ed.shape[1], (frame_len + 4 * sl) * os)].cpu().numpy()
     # sync2frame (signals.py:1709-1741)
     eqargs = {"adaptive_stepsize": True, "Niter": 10, "method": "cma", "Ntaps": 17, "mu": 5e-3}
     eqargs.update(sync_kwargs or {})
     mu_s, synctaps = eqargs.pop("mu"), eqargs.pop("Ntaps")
-    shift, foe, order, _, ok = frame_sync(rx_host, pilot_seq, os, frame_len=frame_len, M_pilot=M_pilot, mu=mu_s,
+    shift, foe, order, _, ok = frame_sync(None, pilot_seq, os, frame_len=frame_len, M_pilot=M_pilot, mu=mu_s,
                                           Ntaps=synctaps, rx_device=Ed, **eqargs)
     shift[shift < 0] += frame_len * os
     shiftf = shift[order]

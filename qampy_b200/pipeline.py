@@ -159,7 +159,7 @@ class SegmentedReceiver:
             return ev[1]
         return None
 
-    def _run_group(self, E, first, nsym, nseg, drop, wxy0, between):
+    def _run_group(self, E, first, nsym, nseg, drop, wxy0, between, stage_done=None):
         cfg = self.cfg
         Ev = device.segment_view(E[:, first * cfg.os:], nseg, nsym, cfg.os, cfg.ntaps)
         L_seg = Ev.shape[2]
@@ -179,6 +179,8 @@ class SegmentedReceiver:
                                    self.syms[stage], cfg.methods[stage], err)
             t and t.record()
             errs.append(err)
+            if stage_done is not None:
+                stage_done(stage, err)      # e.g. run_host: the stage's error array can leave while the chain goes on
         # the final taps of a segment filter its own samples plus the halo on either side (H = 0: the same view)
         H = cfg.bps_halo if first >= cfg.bps_halo else 0
         next_ = nsym + 2 * H
@@ -307,11 +309,11 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, tap
     if rx._streams is None or len(rx._streams["comp"]) < min(nchunks + 3, 19):
         # one compute stream per chunk: the training kernel is latency bound, so the chains of different
         # chunks must run side by side rather than queue behind each other
-        rx._streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
+        rx._streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(), d2h_err=torch.cuda.Stream(),
                            comp=[torch.cuda.Stream() for _ in range(min(nchunks + 3, 19))])
     st = rx._streams
     main = torch.cuda.current_stream()
-    for s_ in [st["h2d"], st["d2h"]] + st["comp"]:
+    for s_ in [st["h2d"], st["d2h"], st["d2h_err"]] + st["comp"]:
         s_.wait_stream(main)
     events, rx.events = rx.events, None
     keep = []
@@ -329,19 +331,28 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, tap
         ev_out = torch.cuda.Event()
         with torch.cuda.stream(comp):
             comp.wait_event(ev_in)
-            res = rx._run_group(E_dev, first, nsym, nseg, drop, wxy0, None)
+            def stage_done(stage, err, seg0=seg0, nseg=nseg):
+                # a stage's training errors leave as soon as the stage is done, on their own copy stream: the download
+                # (the larger direction of the link) starts a training pass after the first upload instead of a
+                # whole chain after it
+                if err is None:
+                    return
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(st["d2h_err"]):
+                    st["d2h_err"].wait_event(ev)
+                    err_host[stage][seg0:seg0 + nseg].copy_(err, non_blocking=True)
+
+            res = rx._run_group(E_dev, first, nsym, nseg, drop, wxy0, None, stage_done if cfg.want_err else None)
             ev_out.record()
         with torch.cuda.stream(st["d2h"]):
             st["d2h"].wait_event(ev_out)
             out_host[seg0:seg0 + nseg].copy_(res["ext"]["out"], non_blocking=True)
             ph_host[seg0:seg0 + nseg].copy_(res["ext"]["ph"], non_blocking=True)
-            if cfg.want_err:
-                for k, e in enumerate(res["err"]):
-                    err_host[k][seg0:seg0 + nseg].copy_(e, non_blocking=True)
         keep.append(res)
         if drop == 0:
             rx.host_carry = res["taps"][-1]                         # taps of the last full segment (carry_taps)
-    for s_ in [st["h2d"], st["d2h"]] + st["comp"]:
+    for s_ in [st["h2d"], st["d2h"], st["d2h_err"]] + st["comp"]:
         main.wait_stream(s_)
     rx.events = events
     rx._keep = keep                                                 # alive until the caller synchronises

@@ -273,3 +273,23 @@ def test_ser_segments_counts_errors_and_resolves_row_rotation_delay():
     want = np.zeros((nseg, 2), np.int64)
     want[2, 1], want[3, 0] = 2, 1
     assert np.array_equal(e.numpy(), want) and int(c.min()) == S
+
+
+def test_rrc_tap_vector_reproduces_the_reference_pulse_shaping():
+    """synth_device._pulse_taps (own restatement of the root-raised-cosine impulse response with its two removable
+    singularities, normalised like core/filter.py:201-205) in a NumPy model of the device pipeline == the reference's
+    rrcos_resample output on the golden symbols (tests/golden/g13_synth.npz)."""
+    import os
+    from qampy_b200.synth_device import _pulse_taps
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g13_synth.npz"))
+    for tag in "ab":
+        M, n, beta, taps, theta, dgd, fb = g[tag + "_par"]
+        n, taps = int(n), int(taps)
+        h = _pulse_taps(taps, 2 * fb, 1 / fb, beta)
+        assert h.max() == 1.0 and np.allclose(h, h[::-1])
+        up = np.zeros((2, 2 * n), complex)
+        up[:, ::2] = g[tag + "_symbols"]
+        nfft = 1 << int(np.ceil(np.log2(2 * n + taps - 1)))
+        y = np.fft.ifft(np.fft.fft(up, nfft, axis=1) * np.fft.fft(h, nfft)[None], axis=1)
+        y = y[:, (taps - 1) // 2:(taps - 1) // 2 + 2 * n]
+        assert np.sqrt(np.mean(np.abs(y - g[tag + "_plain"]) ** 2)) < 1e-12
