@@ -242,6 +242,17 @@ int qb_select_angles_host(int dtype, const void *angles, int64_t p, int64_t A, c
 enum { QB_LAYOUT_THROUGHPUT = 0, QB_LAYOUT_LATENCY = 1 };
 int qb_set_train_layout(int layout);
 
+/* ---- accumulation mode of the blind phase search ------------------------------------------------------
+ * Sets the mode used by the CALLING THREAD's subsequent qb_bps_* calls and returns the previous one.
+ * QB_BPS_EXACT (default): the reference's sequential running sum per test angle in the signal's precision and
+ * its window difference (pythran_dsp.py:26-42) -- phase indices bit-identical to the reference, including where its
+ * fp32 sum has grown to 2e5 after 1e7 symbols and no longer resolves neighbouring angles.
+ * QB_BPS_WINDOWED: every window sum is formed directly from its 2N distances (accumulated in double): the
+ * numerically sound variant, a flagged deviation from the reference's bits; on complex64 input
+ * it follows the reference's complex128 result instead of its complex64 one.                                  */
+enum { QB_BPS_EXACT = 0, QB_BPS_WINDOWED = 1 };
+int qb_set_bps_accumulation(int mode);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t qb_launch_count(void);
 

@@ -39,6 +39,7 @@ struct BpsParams {
     int A, M, n_re, n_im, N;
     int tile_rows, ring_rows;
     int comp_rows;   // 0: one table comp[A]; 1: per-symbol table comp[L][A] per stream (two-stage BPS, :74-77)
+    int windowed;    // QB_BPS_WINDOWED: window sums formed directly from the 2N distances (bps_kernel only)
 };
 
 // Per-axis slicer.  `pairs[f] = (lev[f], lev[f+1])` are the two levels bracketing a value whose
@@ -251,7 +252,21 @@ __global__ void __launch_bounds__(BPS_THREADS) bps_kernel(BpsParams<T> p)
         }
         __syncthreads();
         // ---- phase 2: sequential running sum per angle column + window difference ---------------
-        if (tid < A) {
+        if (p.windowed) {
+            // QB_BPS_WINDOWED: the ring keeps the distances themselves and every window sum is formed directly from
+            // its 2N terms, accumulated in double -- no running sum whose magnitude (2e5 after 1e7 rows) swallows
+            // the differences between neighbouring test angles.  Not the reference's bits: its exact fp32 running
+            // sum is the default mode.  All threads share the (row, angle) pairs of the tile.
+            for (int f = tid; f < nrows * A; f += BPS_THREADS) {
+                const int r = f / A, a = f - r * A;
+                if (i0 + r >= W) {
+                    double acc = 0.0;
+                    for (int w = W - 1; w >= 0; w--)          // oldest row first, like the reference's running sum
+                        acc += (double)ring[(size_t)((slot0 + r - w) & RMASK) * A + a];
+                    dt[(size_t)a * TRP + r] = (T)acc;
+                }
+            }
+        } else if (tid < A) {
             T *xp = ring + (size_t)slot0 * A + tid;
             T *dp = dt + (size_t)tid * TRP;
 #pragma unroll 4
@@ -516,6 +531,17 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
                       const void *angles, int64_t A, const void *lev_re, int64_t n_re, const void *lev_im,
                       int64_t n_im, int64_t N, int32_t *idx, void *ph, void *Eout, cudaStream_t st);
 
+// Accumulation mode of the calling thread's bps launches (qb_set_bps_accumulation): 0 = exact (the reference's
+// sequential fp32 / fp64 running sum, bit-exact indices), 1 = windowed (direct 2N-term sums, more accurate).
+static thread_local int g_bps_accum = 0;
+int bps_accumulation() { return g_bps_accum; }
+int set_bps_accumulation(int mode)
+{
+    const int old = g_bps_accum;
+    g_bps_accum = mode == 1 ? 1 : 0;
+    return old;
+}
+
 template <typename T>
 static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int64_t L,
                       const void *comp, const void *angles, int64_t A, const void *symbols, int64_t M,
@@ -541,6 +567,7 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     p.n_im = (int)n_im;
     p.N = (int)N;
     p.comp_rows = comp_rows;
+    p.windowed = bps_accumulation() == 1;
     const int W = 2 * (int)N;
     // ring: power of two >= TR + 2N rows (so a tile never wraps and slots are a mask away)
     int RR = 2 * BPS_TR;
@@ -562,7 +589,7 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     // default: column-per-lane kernel (bps_fast.cu) where it applies, else the warp-specialised tile kernel;
     // QB_BPS_KERNEL=ws / simple select the tile kernels (tests run all three)
     const char *force = getenv("QB_BPS_KERNEL");
-    if (comp_rows) force = "simple";   // per-symbol angle tables: phase-by-phase kernel only
+    if (comp_rows || p.windowed) force = "simple";   // per-symbol angle tables, windowed sums: phase-by-phase kernel only
     if (sizeof(T) == 4 && !(force && (force[0] == 's' || force[0] == 'w'))) {
         const int rc = bps_fast_dispatch(E, nstream, stream_stride, L, comp, angles, A, lev_re, n_re, lev_im, n_im,
                                          N, idx, ph, Eout, st);

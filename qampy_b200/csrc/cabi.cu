@@ -27,6 +27,7 @@ int set_error(int code, const char *fmt, ...)
 void count_launch(int n) { g_launches += n; }
 
 int set_train_layout(int layout);
+int set_bps_accumulation(int mode);
 int apply_dispatch(int dtype, const void *E, int64_t nseg, int64_t seg_stride, int64_t row_stride,
                    int64_t nmodes, int64_t L, int64_t os, const void *wx, int64_t ntaps,
                    const int64_t *modes, int64_t nsel, void *out, cudaStream_t st);
@@ -200,6 +201,7 @@ int qb_version(void) { return QB_VERSION; }
 const char *qb_last_error(void) { return g_err; }
 int64_t qb_launch_count(void) { return g_launches.load(); }
 int qb_set_train_layout(int layout) { return qb::set_train_layout(layout); }
+int qb_set_bps_accumulation(int mode) { return qb::set_bps_accumulation(mode); }
 
 int qb_device_count(void)
 {

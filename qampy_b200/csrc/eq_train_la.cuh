@@ -110,7 +110,10 @@ __device__ __forceinline__ void tile_gram(const float *tile, int nslots, int nmo
 // no branch sits in the symbol loop.  Whether an alphabet is a grid is found out in the kernel (detect_grid), so
 // both instantiations are launched back to back and each one works on the streams whose alphabet is its kind (all
 // or none of them in practice; the other launch returns after its prologue).  -1: decided at run time.
-template <int LPS, int NQ, int METHOD, int NMASK, int GRID = -1>
+// ADAPT: the reference's adaptive step size (pythran_equalisation.py:12-16, :171-172).  The step size used for symbol
+// i's update depends on the errors of symbols i-1 and i-2 only, so it is known before e_i is and stays off the serial
+// chain of the look-ahead form: c_i = mu_i e_i, mu_{i+1} = adapt_step(mu_i, e_i, e_{i-1}).
+template <int LPS, int NQ, int METHOD, int NMASK, int GRID = -1, bool ADAPT = false>
 __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<float> p, FastGeom g, int warp_smem)
 {
     static_assert(NQ % 2 == 0, "NQ must be even (os = 2: the window moves by one pair per symbol)");
@@ -167,7 +170,8 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
         PI[q] = pack2(w0.y, w1.y);
         if (q >= NP - NMASK) MK[q - (NP - NMASK)] = pack2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
     }
-    const float mu = p.mu[stream];
+    float mu = p.mu[stream];
+    float2 eprev = make_float2(0.f, 0.f);    // ADAPT: error of the symbol before
     const uint32_t errs_addr = smem_u32(errs + grp * g.tile_syms);
     __syncwarp();
     ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);
@@ -346,6 +350,10 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                 const float mu_l = live ? mu : 0.f;     // symbols past the end of the stream: zero step
                 crp = mu_l * e.x;
                 cip = mu_l * e.y;
+                if constexpr (ADAPT) {                  // after the update of symbol i > 0 of an iteration (:171-172)
+                    mu = adapt_step_sel(mu, e, eprev, live && i > 0);
+                    eprev = live ? e : eprev;
+                }
                 const float2 sa = unpack2(sub2(a1, a2)), sb = unpack2(add2(b1, b2));
                 pqr = sa.x + sa.y;
                 pqi = sb.x + sb.y;
@@ -370,14 +378,16 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
                 f32x2 sPR[NP], sPI[NP];
 #pragma unroll
                 for (int q = 0; q < NP; q++) sPR[q] = PR[q], sPI[q] = PI[q];
-                const float scr = crp, sci = cip, spr = pqr, spi = pqi;
+                const float scr = crp, sci = cip, spr = pqr, spi = pqi, smu = mu;
+                const float2 sep = eprev;
                 tile_pass(std::true_type{}, fx_scale, fx_inv);
                 const float seen = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(tmax)));
                 redo = !(seen * fx_scale < 67108864.f);                       // 2^26 per lane; NaN -> redo
                 if (redo) {
 #pragma unroll
                     for (int q = 0; q < NP; q++) PR[q] = sPR[q], PI[q] = sPI[q];
-                    crp = scr, cip = sci, pqr = spr, pqi = spi;
+                    crp = scr, cip = sci, pqr = spr, pqi = spi, mu = smu;
+                    eprev = sep;
                     tmax = 0.f;
                 }
             }
@@ -419,6 +429,7 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
             if (t0 + 2 * q < p.ntaps) wg[t0 + 2 * q] = make_float2(wr.x, wi.x);
             if (t0 + 2 * q + 1 < p.ntaps) wg[t0 + 2 * q + 1] = make_float2(wr.y, wi.y);
         }
+        if (ADAPT && gl == 0) p.mu[stream] = mu;
     }
 }
 
@@ -447,13 +458,13 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     return nq;
 }
 
-template <int LPS, int NQ, int METHOD, int NMASK, int GRID>
+template <int LPS, int NQ, int METHOD, int NMASK, int GRID, bool ADAPT>
 static int launch_la_one(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
     constexpr int GPW = 32 / LPS;
     static bool attr_done = false;
     if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK, GRID>,
+        QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK, GRID, ADAPT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
@@ -463,61 +474,61 @@ static int launch_la_one(const TrainParams<float> &p, const FastGeom &g, size_t 
     // multi-warp CTAs (small launches) ask for more than half of an SM's shared memory so that ONE of them fits an
     // SM and concurrent launches spread over the machine (eq_train_fast.cuh, TRAIN_WPB)
     const size_t dyn = wpb > 1 ? std::max((size_t)wpb * wsm, (size_t)116 * 1024) : wsm;
-    train_la_kernel<LPS, NQ, METHOD, NMASK, GRID><<<(unsigned)((nblk + wpb - 1) / wpb), 32 * wpb, dyn, st>>>(p, g, (int)wsm);
+    train_la_kernel<LPS, NQ, METHOD, NMASK, GRID, ADAPT><<<(unsigned)((nblk + wpb - 1) / wpb), 32 * wpb, dyn, st>>>(p, g, (int)wsm);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }
 
-template <int LPS, int NQ, int METHOD, int NMASK>
+template <int LPS, int NQ, int METHOD, int NMASK, bool ADAPT>
 static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
     if constexpr (METHOD == QB_SBD || METHOD == QB_DD) {
         if (p.nsym_pitch > p.nsym_smem) {    // grid scratch staged: one launch per decision kind (see the kernel)
-            const int rc = launch_la_one<LPS, NQ, METHOD, NMASK, 1>(p, g, smem, st);
+            const int rc = launch_la_one<LPS, NQ, METHOD, NMASK, 1, ADAPT>(p, g, smem, st);
             if (rc != QB_OK) return rc;
         }
-        return launch_la_one<LPS, NQ, METHOD, NMASK, 0>(p, g, smem, st);
+        return launch_la_one<LPS, NQ, METHOD, NMASK, 0, ADAPT>(p, g, smem, st);
     } else {
-        return launch_la_one<LPS, NQ, METHOD, NMASK, -1>(p, g, smem, st);
+        return launch_la_one<LPS, NQ, METHOD, NMASK, -1, ADAPT>(p, g, smem, st);
     }
 }
 
-template <int LPS, int NQ, int METHOD>
+template <int LPS, int NQ, int METHOD, bool ADAPT>
 static int launch_la_pad(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
     constexpr int NP = NQ / 2;
     constexpr int NMLO = NP >= 2 ? 2 : NP;
     const int valid_last = p.ntaps - (g.lpp - 1) * NQ;
     const int need = valid_last <= 0 ? NP : NP - valid_last / 2;
-    if (need == 0) return launch_la<LPS, NQ, METHOD, 0>(p, g, smem, st);
-    if (need <= NMLO) return launch_la<LPS, NQ, METHOD, NMLO>(p, g, smem, st);
-    return launch_la<LPS, NQ, METHOD, NP>(p, g, smem, st);
+    if (need == 0) return launch_la<LPS, NQ, METHOD, 0, ADAPT>(p, g, smem, st);
+    if (need <= NMLO) return launch_la<LPS, NQ, METHOD, NMLO, ADAPT>(p, g, smem, st);
+    return launch_la<LPS, NQ, METHOD, NP, ADAPT>(p, g, smem, st);
 }
 
-template <int LPS, int NQ>
+template <int LPS, int NQ, bool ADAPT>
 static int launch_la_method(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
     switch (p.method) {
     case QB_CMA:
     case QB_SGNCMA:
-        return launch_la_pad<LPS, NQ, QB_CMA>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_CMA, ADAPT>(p, g, smem, st);
     case QB_MCMA:
-        return launch_la_pad<LPS, NQ, QB_MCMA>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_MCMA, ADAPT>(p, g, smem, st);
     case QB_SBD:
-        return launch_la_pad<LPS, NQ, QB_SBD>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_SBD, ADAPT>(p, g, smem, st);
     case QB_DD:
-        return launch_la_pad<LPS, NQ, QB_DD>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_DD, ADAPT>(p, g, smem, st);
     case QB_RDE:
-        if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC>(p, g, smem, st);
-        if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_RDE3>(p, g, smem, st);
-        return launch_la_pad<LPS, NQ, QB_RDE>(p, g, smem, st);
+        if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC, ADAPT>(p, g, smem, st);
+        if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_RDE3, ADAPT>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_RDE, ADAPT>(p, g, smem, st);
     case QB_MRDE:
-        if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC>(p, g, smem, st);
-        if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_MRDE3>(p, g, smem, st);
-        return launch_la_pad<LPS, NQ, QB_MRDE>(p, g, smem, st);
+        if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC, ADAPT>(p, g, smem, st);
+        if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_MRDE3, ADAPT>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, QB_MRDE, ADAPT>(p, g, smem, st);
     default:
-        return launch_la_pad<LPS, NQ, METHOD_GENERIC>(p, g, smem, st);
+        return launch_la_pad<LPS, NQ, METHOD_GENERIC, ADAPT>(p, g, smem, st);
     }
 }
 

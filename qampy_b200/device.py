@@ -126,8 +126,13 @@ class BpsTables:
         self.lev_im = torch.from_numpy(lim).to(device)
 
 
-def bps(E, tables, N, want_idx=True, want_ph=True, want_out=True, use_slicer=True):
-    """Blind phase search over every row of ``E`` (nstream, L).  Returns (Eout, ph, idx)."""
+_BPS_ACCUM = {"exact": 0, "windowed": 1}      # qb_set_bps_accumulation (include/qampy_b200.h)
+
+
+def bps(E, tables, N, want_idx=True, want_ph=True, want_out=True, use_slicer=True, accum="exact"):
+    """Blind phase search over every row of ``E`` (nstream, L).  Returns (Eout, ph, idx).
+    ``accum``: "exact" (default: the reference's sequential running sum, bit-identical indices) or "windowed" (direct
+    2N-term window sums in double: numerically sound on long signals, a flagged deviation from the reference)."""
     _check_cuda(E)
     assert E.dim() == 2 and E.stride(1) == 1
     nstream, L = E.shape
@@ -135,10 +140,15 @@ def bps(E, tables, N, want_idx=True, want_ph=True, want_out=True, use_slicer=Tru
     ph = torch.empty((nstream, L), dtype=_REAL[E.dtype], device=E.device) if (want_ph or want_out) else None
     out = torch.empty((nstream, L), dtype=E.dtype, device=E.device) if want_out else None
     n_re, n_im = (tables.n_re, tables.n_im) if use_slicer else (0, 0)
-    _lib.check(_lib.load().qb_bps_dev(
-        _CODE[E.dtype], _ptr(E), nstream, E.stride(0), L, _ptr(tables.comp), _ptr(tables.angles), tables.A,
-        _ptr(tables.symbols), tables.M, _ptr(tables.lev_re), n_re, _ptr(tables.lev_im), n_im, int(N),
-        _ptr(idx), _ptr(ph), _ptr(out), _stream()))
+    lib = _lib.load()
+    old = lib.qb_set_bps_accumulation(_BPS_ACCUM[accum])
+    try:
+        _lib.check(lib.qb_bps_dev(
+            _CODE[E.dtype], _ptr(E), nstream, E.stride(0), L, _ptr(tables.comp), _ptr(tables.angles), tables.A,
+            _ptr(tables.symbols), tables.M, _ptr(tables.lev_re), n_re, _ptr(tables.lev_im), n_im, int(N),
+            _ptr(idx), _ptr(ph), _ptr(out), _stream()))
+    finally:
+        lib.qb_set_bps_accumulation(old)
     return out, ph, idx
 
 

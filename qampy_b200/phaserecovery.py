@@ -9,7 +9,8 @@ from . import _lib, device
 
 def bps(E, Mtestangles, symbols, N, method="pyt", **kwargs):
     """Blind phase search.  ``method`` is accepted for signature compatibility ("pyt"/"pyx"/"af"/"py"
-    all run the CUDA kernel; anything else raises like the reference)."""
+    all run the CUDA kernel; anything else raises like the reference).  ``accum="windowed"`` (keyword, not in the
+    reference): direct 2N-term window sums instead of the reference's running sum -- see ``device.bps``."""
     if method.lower() not in ("pyx", "af", "py", "pyt", "cuda"):
         raise ValueError("Method needs to be 'pyx', 'py' or 'af'")
     Ein = E
@@ -21,7 +22,7 @@ def bps(E, Mtestangles, symbols, N, method="pyt", **kwargs):
     Ew = np.atleast_2d(E)
     tables = device.BpsTables(int(Mtestangles), symbols, E.dtype.type, dev)
     Ed = torch.from_numpy(np.ascontiguousarray(Ew)).to(dev)
-    out, ph, _ = device.bps(Ed, tables, int(N), want_idx=False)
+    out, ph, _ = device.bps(Ed, tables, int(N), want_idx=False, accum=kwargs.get("accum", "exact"))
     ph = ph.cpu().numpy()
     # keep the SignalObject subclass (and its attributes) of the input, like Ew*np.exp(1j*ph) does
     Eout = np.atleast_2d(Ein).astype(E.dtype)

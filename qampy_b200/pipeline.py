@@ -150,14 +150,26 @@ class SegmentedReceiver:
         self._streams = None
         self.events = None      # set to a list to collect (name, (start, end)) CUDA events per launch
         self.want_idx = True
+        self._nvtx_open = False
 
     def _tic(self, name):
+        # NVTX range per stage (tracing): costs nothing without a profiler attached; the range
+        # is closed by _toc / the next _tic
+        if self._nvtx_open:
+            torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_push("qampy_b200." + name)
+        self._nvtx_open = True
         if self.events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
             self.events.append((name, ev))
             return ev[1]
         return None
+
+    def _toc(self):
+        if self._nvtx_open:
+            torch.cuda.nvtx.range_pop()
+            self._nvtx_open = False
 
     def _run_group(self, E, first, nsym, nseg, drop, wxy0, between, stage_done=None):
         cfg = self.cfg
@@ -197,6 +209,7 @@ class SegmentedReceiver:
         if idx is None:
             idx = ph
         shp = (nseg, self.nmodes, next_)
+        self._toc()
         ext = dict(eq=eq, out=out.reshape(shp), ph=ph.reshape(shp), idx=idx.reshape(shp))
         own = {k: v[:, :, H:H + nsym] for k, v in ext.items()}         # the segment's own symbols (views)
         return dict(own, ext=ext, halo=H, taps=w, err=errs, first=first, nsym=nsym, nseg=nseg, drop=drop)
@@ -222,6 +235,7 @@ class SegmentedReceiver:
             device.train_equaliser(Ev, A, cfg.niter[stage], cfg.os, mu, w, None, False, self.syms[stage],
                                    cfg.methods[stage], None, layout=cfg.acq_layout)
             t and t.record()
+        self._toc()
         return w[0]
 
     @staticmethod

@@ -477,3 +477,71 @@ def test_training_is_scale_free_like_the_reference(env, layout, scale, spike):
         # 3e-5 relative == the 1e-5 absolute bound of the unit-power tests at their error level (rms 0.32)
         assert rms(err.cpu().numpy() - er) < 3e-5 * rms(er), (method, scale, rms(err.cpu().numpy() - er), rms(er))
         assert np.max(np.abs(w.cpu().numpy() - wr)) < 3e-5 * np.max(np.abs(wr)), (method, scale)
+
+
+@pytest.mark.parametrize("layout", ["throughput", "latency"])
+@pytest.mark.parametrize("M,ntaps,method", [(64, 45, "mcma"), (64, 45, "mrde"), (16, 21, "cma"), (16, 21, "sbd"),
+                                             (64, 13, "mddma"), (16, 21, "rde")])
+def test_adaptive_step_size_in_the_lookahead_trainer(env, layout, M, ntaps, method):
+    """adaptive_stepsize=True (pythran_equalisation.py:12-16, :171-172) in the look-ahead kernels of both layouts: the
+    step size of a symbol's update depends on the two errors before it, so it stays off the serial chain; errors, taps
+    and the final step size follow the oracle over two training iterations, three segments, per-stream step sizes."""
+    t = env.torch
+    nseg, S, niter = 3, 2500, 2
+    E, _ = env.synth.synth_numpy(M, nseg * S + 100, seed=3 * M + ntaps, snr_db=25.0)
+    Ed = t.from_numpy(E).to(env.dev)
+    Ev = env.device.segment_view(Ed, nseg, S, 2, ntaps)
+    tr = env.theory.cal_training_symbol_len(2, ntaps, Ev.shape[2])
+    sy = env.theory.reshape_symbols(None, method, M, np.complex64, 2)
+    w = t.from_numpy(np.tile(env.theory.init_taps(ntaps, 2, np.complex64), (nseg, 1, 1, 1))).to(env.dev)
+    mu = t.full((nseg, 2), 4e-3, dtype=t.float32, device=env.dev)
+    err = t.zeros((nseg, 2, tr * niter), dtype=t.complex64, device=env.dev)
+    env.device.train_equaliser(Ev, tr, niter, 2, mu, w, None, True, t.from_numpy(sy).to(env.dev), method, err, layout=layout)
+    Es = np.stack([E[:, s * S * 2: s * S * 2 + Ev.shape[2]] for s in range(nseg)])
+    wr = np.tile(env.theory.init_taps(ntaps, 2, np.complex64), (nseg, 1, 1, 1))
+    mur = np.zeros((nseg, 2), np.float32)
+    er = np.zeros((nseg, 2, tr * niter), np.complex64)
+    for m in range(2):        # one step size per stream: the oracle trains the modes one by one
+        e_m, _, mu_m = env.co.train_segments(Es, tr, niter, 2, 4e-3, wr, [m], True, sy, method, mu_shared=False)
+        er[:, m] = e_m[:, m]
+        mur[:, m] = mu_m
+    assert rms(err.cpu().numpy() - er) < 1e-5 * max(1.0, rms(er))
+    assert np.max(np.abs(w.cpu().numpy() - wr)) < 2e-5
+    assert np.max(np.abs(mu.cpu().numpy() / mur - 1)) < 1e-4 and np.all(mur < 4e-3)
+
+
+def test_bps_windowed_accumulation_follows_the_double_precision_reference(env):
+    """qb_set_bps_accumulation(QB_BPS_WINDOWED): window sums formed directly from their 2N terms.  On a long complex64
+    stream the reference's fp32 running sum (the default, bit-exact mode) has lost the resolution to tell neighbouring
+    test angles apart; the windowed mode follows what the reference computes in complex128 on the same samples.  The
+    mode is per calling thread and the default is untouched."""
+    from qampy_b200 import _lib
+    t = env.torch
+    lib = _lib.load()
+    assert lib.qb_set_bps_accumulation(1) == 0 and lib.qb_set_bps_accumulation(0) == 1
+    M, A, N, L = 64, 64, 45, 600000
+    rng = np.random.default_rng(5)
+    al = env.theory.normalised_symbols(M)
+    x = al[rng.integers(0, M, L)] * np.exp(1j * np.cumsum(rng.standard_normal(L) * 2e-3))
+    x = (x + 0.03 * (rng.standard_normal(L) + 1j * rng.standard_normal(L))).astype(np.complex64)
+    idx64 = env.co.bps_streams(x[None], env.theory.bps_test_angles(A, np.float32), al.astype(np.complex64), N)[0]
+    idx128 = env.co.bps_streams(x[None].astype(np.complex128), env.theory.bps_test_angles(A, np.float64), al, N)[0]
+    tabs = env.device.BpsTables(A, al.astype(np.complex64), np.complex64, env.dev)
+    xd = t.from_numpy(x).to(env.dev)[None]
+    _, _, exact = env.device.bps(xd, tabs, N)
+    _, ph_w, windowed = env.device.bps(xd, tabs, N, accum="windowed")
+    exact, windowed = exact.cpu().numpy()[0], windowed.cpu().numpy()[0]
+    assert np.array_equal(exact, idx64)                                     # default mode: the reference's c64 bits
+    tail = slice(L - 200000, L - N)
+    flips64 = np.mean(idx64[tail] != idx128[tail])
+    flips_w = np.mean(windowed[tail] != idx128[tail])
+    print("late-stream index disagreement with the c128 reference: exact fp32 %.2e, windowed %.2e" % (flips64, flips_w))
+    assert flips_w < 2e-3 and flips_w < 0.2 * flips64 + 1e-4
+    assert np.mean(windowed[N:L - N] != idx128[N:L - N]) < 2e-3
+    assert np.all(windowed[:N] == 0) and np.all(windowed[L - N:] == 0) and np.isfinite(ph_w.cpu().numpy()).all()
+    # brute-force search (no grid slicer) and complex128 input take the same mode
+    _, _, w_bf = env.device.bps(xd, tabs, N, accum="windowed", use_slicer=False)
+    assert np.array_equal(w_bf.cpu().numpy()[0], windowed)
+    tabs128 = env.device.BpsTables(A, al, np.complex128, env.dev)
+    _, _, w128 = env.device.bps(t.from_numpy(x.astype(np.complex128)).to(env.dev)[None], tabs128, N, accum="windowed")
+    assert np.mean(w128.cpu().numpy()[0][N:L - N] != idx128[N:L - N]) < 1e-4

@@ -97,14 +97,16 @@ def test_pilot_receiver_on_cuda(golden):
     g = golden("g9_pilot_rx")
     be = _cuda_backend()
     rx3, shiftf = _run_chain(g, be, 1e-4, 1e-4)
-    # the batched window trainer equals per-window equalise_signal calls
+    # the batched window trainer (throughput layout of the trainer) equals per-window equalise_signal calls (one
+    # capture each: latency layout -- another kernel since the adaptive step size runs in the look-ahead form, so
+    # equal to rounding, not bit for bit)
     starts = np.arange(2, 9) * 512
     taps, errs = be.equalise_windows(g["rx"], starts, 1024, 2, 5e-3, 4, Ntaps=17, Niter=10, method="cma",
                                      adaptive_stepsize=True)
     for k, s0 in enumerate(starts):
         w, e = be.equalise_signal(g["rx"][:, s0:s0 + 1024], 2, 5e-3, 4, Ntaps=17, Niter=10, method="cma",
                                   adaptive_stepsize=True)
-        assert np.array_equal(w, taps[k]) and np.array_equal(e, errs[k])
+        assert np.max(np.abs(w - taps[k])) < 1e-5 and rms(e - errs[k]) < 1e-5
     # several frames: frame 0 from centre-spike taps, the others from frame 0's taps
     fl, osf = int(g["frame_len"]), int(g["os"])
     taps_all, eq_all, _ = pilots.pilot_equaliser_nframes(rx3, g["pilot_seq"], shiftf, osf, fl, (1e-3, 1e-3), 45,
