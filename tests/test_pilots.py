@@ -151,8 +151,8 @@ def _payload_ser(eq_frames, d, fl, sl, M, tx_frames):
 
 @pytest.mark.gpu
 def test_batched_frames_equal_frame_by_frame():
-    """pilot_equaliser_nframes: the frames trained side by side in one launch per stage give bit for bit what
-    the frame-by-frame loop gives, and the chain demodulates a synthetic pilot-framed signal."""
+    """pilot_equaliser_nframes: the frames trained side by side in one launch per stage give what
+    the frame-by-frame loop gives (to rounding: the two run different layouts of the trainer), and the chain demodulates a synthetic pilot-framed signal."""
     from qampy_b200 import synth
     be = _cuda_backend()
     M, fl, sl, rat, nfr = 16, 2 ** 13, 512, 32, 6
@@ -171,11 +171,12 @@ def test_batched_frames_equal_frame_by_frame():
     for f in range(1, 5):       # every later frame == pilot_equaliser on that frame alone from frame 0's taps
         t1, e1 = pilots.pilot_equaliser(*args, synctaps=17, foe_comp=False, wxinit=t_b[0].copy(), frame=f,
                                         methods=("cma", "sbd"), backend=be)
-        assert np.array_equal(t1, t_b[f]) and np.array_equal(e1, eq_b[:, f * fl:(f + 1) * fl]), f
+        # (alone: one capture -> latency layout of the trainer; in the batch: throughput layout -- equal to rounding)
+        assert np.max(np.abs(t1 - t_b[f])) < 1e-5 and rms(e1 - eq_b[:, f * fl:(f + 1) * fl]) < 1e-5, f
     # the reference's own loop warm-starts frame f from frame f-1 (its wxinit array is trained in place,
     # equalisation.py:547); batched=False reproduces that chain, and both demodulate
     t_s, eq_s, _ = pilots.pilot_equaliser_nframes(*args, batched=False, **kw)
-    assert np.array_equal(eq_s[:, :fl], eq_b[:, :fl])      # frame 0 is the same in both
+    assert rms(eq_s[:, :fl] - eq_b[:, :fl]) < 1e-5         # frame 0 is the same in both
     # (a 450-symbol pilot training occasionally leaves a frame unconverged -- the algorithm's, and the
     # reference's, behaviour; the chain as a whole has to demodulate)
     assert sorted(_payload_ser(eq_b, d, fl, sl, M, range(5)))[3] < 2e-3
@@ -186,7 +187,7 @@ def test_batched_frames_equal_frame_by_frame():
 def test_full_size_c4_pilot_receiver():
     """BASELINE config C4 at full size: dual-pol 256-QAM, 61 frames of 2**16 symbols (4e6 symbols), pilot sequence
     2**10, one phase pilot per 32, ntaps 45 (17 for the frame search).  Frame sync + pilot equaliser over 59
-    frames side by side + pilot CPE: the frames demodulate, and a frame taken out of the batch is bit-identical
+    frames side by side + pilot CPE: the frames demodulate, and a frame taken out of the batch is identical to rounding
     to the same frame equalised alone and matches the CPU oracle."""
     import torch
     from qampy_b200 import synth
@@ -209,7 +210,7 @@ def test_full_size_c4_pilot_receiver():
     f = 41
     t1, e1 = pilots.pilot_equaliser(rx3, seq, shiftf, 2, fl, (1e-3, 1e-3), 45, synctaps=17, foe_comp=False,
                                     wxinit=taps[0].copy(), frame=f, methods=("cma", "sbd"), backend=be)
-    assert np.array_equal(t1, taps[f]) and np.array_equal(e1, eq[:, f * fl:(f + 1) * fl])
+    assert np.max(np.abs(t1 - taps[f])) < 1e-5 and rms(e1 - eq[:, f * fl:(f + 1) * fl]) < 1e-5
     t2, e2 = pilots.pilot_equaliser(rx3, seq, shiftf, 2, fl, (1e-3, 1e-3), 45, synctaps=17, foe_comp=False,
                                     wxinit=taps[0].copy(), frame=f, methods=("cma", "sbd"), backend=ORACLE)
     assert np.max(np.abs(t2 - taps[f])) < 1e-4 and rms(e2 - e1) < 1e-4
