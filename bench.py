@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--acq-layout", default="latency", choices=["latency", "throughput"])
     ap.add_argument("--no-err", action="store_true", help="do not produce / download the per-symbol training errors "
                                                           "(the reference always returns them)")
-    ap.add_argument("--chunks", type=int, default=6, help="host<->device overlap chunks of the e2e path (the last one "
+    ap.add_argument("--chunks", type=int, default=8, help="host<->device overlap chunks of the e2e path (the last one "
                                                           "is cut into 1/2 + 1/4 + 1/4 unless --no-taper)")
     ap.add_argument("--ntaps", type=int, default=45)
     ap.add_argument("--M", type=int, default=64)
