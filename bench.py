@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the single-capture drop-in records (script shapes)")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record (one 1e9-sample capture over the ranks)")
     ap.add_argument("--no-taper", action="store_true", help="e2e path: do not cut the last chunk into 1/2 + 1/4 + 1/4")
     return ap.parse_args()
@@ -428,6 +429,43 @@ def c5_record(a, rank, world, dev):
             "symbols_compared": int(stats[1].item())}
 
 
+def dropin_records(dev):
+    """The equaliser calls of the reference's Scripts/*_equalisation.py (their dtype, length, taps, methods, step-size
+    rule) as ONE capture through the drop-in API (qampy_b200.equalisation.dual_mode_equalisation: host array in, host
+    arrays out) against the oracle port with the reference's flags.  The reference's own call shape is one serial
+    stream per mode: this is where the GPU path is NOT faster; reported so that the headline
+    is not mistaken for it."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_oracle as co
+    from qampy_b200 import equalisation as eq, synth
+    shapes = (("64_qam_equalisation.py", 64, 2 ** 17, 13, (0.19e-2, 0.19e-2), ("mcma", "mddma"), (True, True)),
+              ("mrde_equaliser.py", 16, 2 ** 18, 30, (1e-3, 0.5e-3), ("mcma", "mrde"), (False, False)),
+              ("32_qam_equalisation.py", 32, 10 ** 6, 11, (1e-3, 1e-3), ("mcma", "sbd"), (False, False)))
+    out = []
+    for name, M, nsym, ntaps, mu, methods, adaptive in shapes:
+        E64, _ = synth.synth_signal(M, nsym, seed=3, snr_db=25.0, beta=0.01, theta=np.pi / 3, dgd=30e-12, device=dev)
+        for dt in (np.complex128, np.complex64):
+            E = E64.cpu().numpy().astype(dt)
+            tg = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                rg = eq.dual_mode_equalisation(E, 2, mu, M, Ntaps=ntaps, methods=methods, adaptive_stepsize=adaptive)
+                torch.cuda.synchronize()
+                tg.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            rc = co.dual_mode_equalisation(E, 2, mu, M, Ntaps=ntaps, methods=methods, adaptive_stepsize=adaptive,
+                                           kind="fast_native")
+            tc = time.perf_counter() - t0
+            out.append({"script": name, "dtype": np.dtype(dt).name, "symbols": nsym, "ntaps": ntaps,
+                        "methods": list(methods), "adaptive": list(adaptive), "gpu_s": min(tg), "cpu_s": tc,
+                        "speedup": tc / min(tg),
+                        "rms_diff": float(np.sqrt(np.mean(np.abs(rg[0] - rc[0]) ** 2)))})
+    return out
+
+
 def run_b200(a, rank, local_rank, world):
     import numpy as np
     import torch
@@ -680,6 +718,11 @@ def run_b200(a, rank, local_rank, world):
                         "warm-up steps), --start acquire once per capture inside every timed step"}
         if c5 is not None:
             line["c5"] = c5
+        if world == 1 and not a.no_dropin:
+            try:
+                line["dropin"] = dropin_records(dev)
+            except Exception as exc:
+                line["dropin"] = {"error": repr(exc)}
         if world == 1 and not a.no_cpu_baseline:
             try:
                 line["cpu_baseline"], _ = cpu_baseline(a, a.cpu_seconds)

@@ -577,14 +577,11 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     if (smem > 200 * 1024) return set_error(QB_ERR_UNSUPPORTED, "bps: 2N*A too large for the shared-memory ring");
     p.tile_rows = BPS_TR;
     p.ring_rows = RR;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[sizeof(T) == 8]) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(bps_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
-        QB_CUDA_CHECK(cudaFuncSetAttribute(bps_ws_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
-        attr_done[sizeof(T) == 8] = true;
-    }
+    // set on every launch: the attribute belongs to the device that is current, and it is cheap
+    QB_CUDA_CHECK(cudaFuncSetAttribute(bps_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+    QB_CUDA_CHECK(cudaFuncSetAttribute(bps_ws_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
     if (nstream > 2147483647LL) return set_error(QB_ERR_UNSUPPORTED, "bps: too many streams");
     // default: column-per-lane kernel (bps_fast.cu) where it applies, else the warp-specialised tile kernel;
     // QB_BPS_KERNEL=ws / simple select the tile kernels (tests run all three)

@@ -357,12 +357,9 @@ static size_t fast_smem_bytes(int NW, int A, int n_re, int n_im, int N)
 template <int NW>
 static int launch_fast(const BpsFastParams &p, int64_t nstream, size_t smem, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(bps_fast_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
-        attr_done = true;
-    }
+    // set on every launch: the attribute belongs to the device that is current, and it is cheap
+    QB_CUDA_CHECK(cudaFuncSetAttribute(bps_fast_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
     bps_fast_kernel<NW><<<(unsigned)nstream, 32 * NW, smem, st>>>(p);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "qb_common.cuh"
@@ -114,24 +115,29 @@ struct DevBuf {
 
 static int host_stream(cudaStream_t *st)
 {
-    static cudaStream_t s = nullptr;
-    static bool pool_done = false;
+    // one library-owned stream (and one memory-pool set-up) per DEVICE, created under a lock: streams and pools belong
+    // to the device that is current when they are made, and two threads may make their first call at the same time
+    static std::mutex mtx;
+    static cudaStream_t streams[64] = {nullptr};
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return set_error(QB_ERR_CUDA, "no CUDA device available (%s); qampy_b200 has no CPU fallback",
                          e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    if (!s) QB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    if (!pool_done) {
-        int dev = 0;
+    int dev = 0;
+    QB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(QB_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(mtx);
+    if (!streams[dev]) {
+        cudaStream_t s = nullptr;
+        QB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         cudaMemPool_t pool;
-        QB_CUDA_CHECK(cudaGetDevice(&dev));
         QB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
         uint64_t thr = ~0ull;  // keep freed scratch cached between calls
         QB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        pool_done = true;
+        streams[dev] = s;
     }
-    *st = s;
+    *st = streams[dev];
     return QB_OK;
 }
 

@@ -279,13 +279,10 @@ static int launch_apply(const void *E, int64_t nseg, int64_t seg_stride, int64_t
         const int npair_w = ((int)ntaps + 1) / 2;
         size_t smem = (size_t)(2 * (A22_TO + npair_w) + 4 * npair_w) * sizeof(float4);
         if (smem <= 200 * 1024) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                QB_CUDA_CHECK(cudaFuncSetAttribute(apply_2x2_os2_kernel,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   200 * 1024));
-                attr_done = true;
-            }
+            // set on every launch: the attribute belongs to the device that is current, and it is cheap
+            QB_CUDA_CHECK(cudaFuncSetAttribute(apply_2x2_os2_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               200 * 1024));
             dim3 grid((unsigned)((N + A22_TO - 1) / A22_TO), (unsigned)nseg);
             apply_2x2_os2_kernel<<<grid, A22_THREADS, smem, st>>>(p);
             count_launch();
@@ -317,12 +314,9 @@ static int launch_apply(const void *E, int64_t nseg, int64_t seg_stride, int64_t
     if (R < 1)
         return set_error(QB_ERR_UNSUPPORTED, "apply_filter_to_signal: nmodes*ntaps*os too large for shared memory");
     p.R = R;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[sizeof(T) == 8]) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(apply_generic_kernel<T>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done[sizeof(T) == 8] = true;
-    }
+    // set on every launch: the attribute belongs to the device that is current, and it is cheap
+    QB_CUDA_CHECK(cudaFuncSetAttribute(apply_generic_kernel<T>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const long long TO = (long long)APPLY_THREADS * R;
     const long long nblk = (N + TO - 1) / TO;
     if (nseg > 65535 || nblk > 2147483647LL)

@@ -143,12 +143,9 @@ __global__ void __launch_bounds__(32) train_warp_kernel(TrainParams<T> p)
 template <typename T, int NQ>
 static int launch_train_nq(const TrainParams<T> &p, long long nstreams, size_t smem, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(train_warp_kernel<T, NQ>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    // set on every launch: the attribute belongs to the device that is current, and it is cheap
+    QB_CUDA_CHECK(cudaFuncSetAttribute(train_warp_kernel<T, NQ>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     train_warp_kernel<T, NQ><<<(unsigned)nstreams, 32, smem, st>>>(p);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());

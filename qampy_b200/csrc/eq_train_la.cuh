@@ -462,12 +462,9 @@ template <int LPS, int NQ, int METHOD, int NMASK, int GRID, bool ADAPT>
 static int launch_la_one(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
     constexpr int GPW = 32 / LPS;
-    static bool attr_done = false;
-    if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK, GRID, ADAPT>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    // set on every launch: the attribute belongs to the device that is current, and it is cheap
+    QB_CUDA_CHECK(cudaFuncSetAttribute(train_la_kernel<LPS, NQ, METHOD, NMASK, GRID, ADAPT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const long long nblk = (p.nstreams + GPW - 1) / GPW;
     const size_t wsm = (smem + 15) & ~(size_t)15;   // per-warp slice, 16-byte aligned
     const int wpb = (int)(train_warps_per_cta(nblk) < nblk ? train_warps_per_cta(nblk) : nblk);   // never more warps (or shared memory) than streams need

@@ -137,12 +137,9 @@ int pilot_cpe_dispatch(int dtype, const void *E, int64_t nrows, int64_t row_stri
     const size_t ts = dtype == QB_C64 ? 4 : 8;
     const size_t smem = (((size_t)(2 * nph + 1) * ts + 7) & ~(size_t)7) + (size_t)(nph - navg + 1) * 8;
     if (smem > 200 * 1024) return set_error(QB_ERR_UNSUPPORTED, "pilot_cpe: too many pilots per row for shared memory");
-    static bool attr_done = false;
-    if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(pilot_cpe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        QB_CUDA_CHECK(cudaFuncSetAttribute(pilot_cpe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    // set on every launch: the attribute belongs to the device that is current, and it is cheap
+    QB_CUDA_CHECK(cudaFuncSetAttribute(pilot_cpe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    QB_CUDA_CHECK(cudaFuncSetAttribute(pilot_cpe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (dtype == QB_C64)
         pilot_cpe_kernel<float><<<(unsigned)nrows, CPE_THREADS, smem, st>>>(
             (const float2 *)E, row_stride, nlen, (const long long *)pidx, (const float2 *)pilots, pilot_stride, (int)nph,

@@ -206,12 +206,9 @@ static int vv_launch(const void *E, int64_t nrows, int64_t row_stride, int64_t L
     T *tile_prev = reinterpret_cast<T *>(work);                        // T first: keeps doubles 8-byte aligned
     int *tile_turns = reinterpret_cast<int *>(tile_prev + (size_t)nrows * ntiles);
     const size_t smem = (size_t)(VV_TILE + N) * sizeof(double2) + (size_t)(VV_TILE + 1) * sizeof(T);
-    static bool attr_done = false;
-    if (!attr_done) {
-        QB_CUDA_CHECK(cudaFuncSetAttribute(vv_phase_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)((VV_TILE + VV_MAX_N) * sizeof(double2) + (VV_TILE + 1) * sizeof(T))));
-        attr_done = true;
-    }
+    // set on every launch: the attribute belongs to the device that is current, and it is cheap
+    QB_CUDA_CHECK(cudaFuncSetAttribute(vv_phase_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((VV_TILE + VV_MAX_N) * sizeof(double2) + (VV_TILE + 1) * sizeof(T))));
     dim3 grid((unsigned)ntiles, (unsigned)nrows);
     vv_phase_kernel<T><<<grid, VV_THREADS, smem, st>>>((const cx<T> *)E, row_stride, L, N, M, (T *)ph, ph_stride,
                                                        tile_turns, tile_prev, ntiles);

@@ -332,16 +332,17 @@ def _pilot_frames_batched(be, rx_signal, pilot_seq, shiftfctrs, os, frame_len, m
 
 
 def pilot_equaliser_nframes(rx_signal, pilot_seq, shiftfctrs, os, frame_len, mu, Ntaps, synctaps=17, apply=True,
-                            foe_comp=True, frames=(0,), wxinit=None, backend=None, batched=True, **eqkwargs):
+                            foe_comp=True, frames=(0,), wxinit=None, backend=None, batched=False, **eqkwargs):
     """Pilot-based equalisation over several frames: array form of ``pilot_equaliser_nframes`` (:336-397).
     Frame 0 starts from ``wxinit`` (centre spike by default); every frame after it starts from frame 0's taps
     -- those frames are independent of one another and, without frequency offset estimation, are trained and
     filtered side by side (``batched``; one launch per stage for all of them).
 
-    ``batched=False`` is the reference's loop as it actually behaves: its ``wxinit`` array is trained in place
-    by every call (``equalisation.py:547``), so frame f warm-starts from frame f-1's pre-convergence taps
-    rather than from frame 0's.  ``batched=True`` (default) is what that loop reads like -- every frame from
-    frame 0's taps -- and frame f then equals ``pilot_equaliser(frame=f, wxinit=<copy of frame 0's taps>)``.
+    ``batched=False`` (default: the drop-in behaviour) is the reference's loop as it actually behaves: its ``wxinit``
+    array is trained in place by every call (``equalisation.py:547``), so frame f warm-starts from frame f-1's
+    pre-convergence taps rather than from frame 0's.  ``batched=True`` (opt-in; what ``pilot_receiver`` uses) is what
+    that loop reads like -- every frame from frame 0's taps -- and frame f then equals ``pilot_equaliser(frame=f,
+    wxinit=<copy of frame 0's taps>)``: independent frames, one launch per stage for all of them.
     Returns (list of taps per frame, equalised frames stacked along time or None, list of frequency offsets)."""
     if shiftfctrs is None:
         raise ValueError("The signal has to be synchronised to the frame first")

@@ -3,7 +3,7 @@
 # Run on the GPU box:  bash scratch/seg_sweep.sh > gpurun_out/seg_sweep.jsonl
 for seg in 8454 32768 131072 262144; do
   for start in cold stream acquire; do
-    python bench.py --seg $seg --start $start --no-cpu-baseline --no-c5 --no-e2e --steps 5 --warmup 3 2>/dev/null | python -c "
+    python bench.py --seg $seg --start $start --no-cpu-baseline --no-c5 --no-dropin --no-e2e --steps 5 --warmup 3 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 w=d.get('withheld') or {}

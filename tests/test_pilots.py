@@ -203,7 +203,7 @@ def test_full_size_c4_pilot_receiver():
     rx3 = pilots.corr_foe(al, foe, 2)
     frames = list(range(59))
     taps, eq, _ = pilots.pilot_equaliser_nframes(rx3, seq, shiftf, 2, fl, (1e-3, 1e-3), 45, synctaps=17, foe_comp=False,
-                                                 frames=frames, methods=("cma", "sbd"), backend=be)
+                                                 frames=frames, methods=("cma", "sbd"), backend=be, batched=True)
     assert eq.shape == (2, 59 * fl) and np.isfinite(eq).all()
     ser = _payload_ser(eq[:, :4 * fl], d, fl, sl, M, range(4)) + _payload_ser(eq[:, 57 * fl:59 * fl], d, fl, sl, M, (57, 58))
     assert sorted(ser)[4] < 5e-2, ser      # 256-QAM at 35 dB with pilot CPE: about 1-2 %
