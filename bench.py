@@ -42,7 +42,7 @@ TRAFFIC_TRAIN, TRAFFIC_BPS = 326.1e6, 352.3e6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
@@ -744,7 +744,14 @@ def resolve_segments(a):
     if a.seg < 0:
         from qampy_b200 import pipeline
         cfg = pipeline.ReceiverConfig(M=a.M, ntaps=a.ntaps, os=2)
-        a.seg = pipeline.balanced_segment_symbols(2 * a.nsym, cfg, target=8192)
+        n_sm = 148
+        try:
+            import torch
+            if torch.cuda.is_available():     # the CPU arm has no device: it uses the B200's count, like the GPU arm
+                n_sm = torch.cuda.get_device_properties(int(os.environ.get("LOCAL_RANK", "0"))).multi_processor_count
+        except Exception:
+            pass
+        a.seg = pipeline.balanced_segment_symbols(2 * a.nsym, cfg, target=8192, n_sm=n_sm)
     return a
 
 

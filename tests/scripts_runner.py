@@ -35,16 +35,26 @@ class _Anything:
         return iter(())
 
 
+def stub_module(name):
+    """A module object whose every public attribute is an :class:`_Anything` (dunder look-ups fail as usual)."""
+    stub = _Anything()
+    m = types.ModuleType(name)
+
+    def _getattr(attr):
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+        return stub
+    m.__getattr__ = _getattr
+    return m
+
+
 @contextlib.contextmanager
 def _stubbed_matplotlib():
     saved = {k: v for k, v in sys.modules.items() if k == "matplotlib" or k.startswith("matplotlib.")}
     for k in saved:
         del sys.modules[k]
-    stub = _Anything()
     for name in ("matplotlib", "matplotlib.pylab", "matplotlib.pyplot"):
-        m = types.ModuleType(name)
-        m.__getattr__ = lambda attr, _s=stub: _s
-        sys.modules[name] = m
+        sys.modules[name] = stub_module(name)
     sys.modules["matplotlib"].pylab = sys.modules["matplotlib.pylab"]
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     try:

@@ -51,6 +51,9 @@ class OracleLib:
                                 symbols, K, method, mu_shared, err):
         ct, rt = _CT[code]
         self.calls.append("train")
+        if method not in self.names:
+            return self._train_real(ct, rt, E, nmodes, L, TrSyms, Niter, os_, mu, wx, ntaps, modes, nsel, adaptive,
+                                    symbols, K, method, err)
         Ea = _arr(E, (nmodes, L), ct)
         wa = _arr(wx, (nmodes, nmodes, ntaps), ct)
         ma = _arr(modes, (nsel,), np.int64)
@@ -58,6 +61,26 @@ class OracleLib:
         mua = _arr(mu, (1,), rt)
         e, w, m = self.co.train_equaliser(Ea, TrSyms, Niter, os_, mua[0], wa.copy(), ma.copy(), bool(adaptive), sa,
                                           self.names[method], mu_shared=bool(mu_shared))
+        wa[...] = w
+        mua[0] = m
+        if _addr(err):
+            _arr(err, (nmodes, TrSyms * Niter), ct)[...] = e
+        return 0
+
+    def _train_real(self, ct, rt, E, nmodes, L, TrSyms, Niter, os_, mu, wx, ntaps, modes, nsel, adaptive, symbols, K,
+                    method, err):
+        """real-valued methods (QB_*_REAL ids): the caller hands real data widened to complex with zero imaginary
+        parts (qampy_b200.pythran_equalisation.train_equaliser_realvalued); the oracle's NumPy restatement of
+        pythran_equalisation.py:80-128 works on the real parts"""
+        from qampy_b200 import pythran_equalisation as q_pe
+        name = {v: k for k, v in q_pe._REAL_METHODS.items()}[method]
+        Ea = np.ascontiguousarray(_arr(E, (nmodes, L), ct).real)
+        wa = _arr(wx, (nmodes, nmodes, ntaps), ct)
+        wr = np.ascontiguousarray(wa.real)
+        sa = np.ascontiguousarray(_arr(symbols, (nmodes, K), ct).real)
+        mua = _arr(mu, (1,), rt)
+        e, w, m = self.co.train_equaliser_realvalued(Ea, TrSyms, Niter, os_, mua[0], wr, _arr(modes, (nsel,), np.int64).copy(),
+                                                     bool(adaptive), sa, name)
         wa[...] = w
         mua[0] = m
         if _addr(err):
@@ -110,6 +133,15 @@ class OracleLib:
         for a in range(0, n, 32768):       # the oracle forms (chunk, M/2) distance tables
             o[a:a + 32768] = self.co.soft_l_value_demapper(_arr(rx, (n,), ct)[a:a + 32768], num_bits, snr, bm,
                                                             minmax=bool(minmax))
+        return 0
+
+    def qb_bps_rows_host(self, code, E, nstream, L, comp, angles, A, symbols, M, N, idx, ph, Eout):
+        """per-symbol angle table comp[L][A] (pythran_dsp.py:74-77): the oracle's C entry point with L table rows"""
+        self.calls.append("bps_rows")
+        assert nstream == 1 and not _addr(ph) and not _addr(Eout)
+        fn = getattr(self.co.lib("strict"), "qo_bps" + ("_f32" if code == 0 else "_f64"))
+        rc = fn(_addr(E), 1, L, L, _addr(comp), L, A, _addr(symbols), M, N, _addr(idx))
+        assert rc == 0
         return 0
 
     def qb_select_angles_host(self, code, angles, p, A, idx, L, out):
