@@ -6,7 +6,8 @@
 * ``test/test_equalisation.py`` -- ``TestReturnObject`` / ``TestEqualisation`` (:10-46);
 * ``test/test_signal_recover_functional.py`` -- ``TestLMS`` (:162-185): sbd, mddma, dd, sbd_data, rde, mrde and the
   real-valued dd_real / dd_data_real, complex64 and complex128, ``adaptive_stepsize=True``, ``Niter=3``: at most three
-  wrong symbols.  ``QB_REF_SUITE_FULL=1`` adds ``TestDualMode`` and ``TestCMA::test_pol_rot`` (2 minutes).
+  wrong symbols.  ``QB_REF_SUITE_FULL=1`` adds ``TestDualMode`` (without ``test_pmd_phase``, which fails on the unpatched reference
+  itself) and ``TestCMA::test_pol_rot`` (2 minutes).
 
 Each selection runs in a subprocess with ``tests/ref_patch_plugin.py`` (patch + repeatable randomness; in this
 container the shared library is the oracle-backed stand-in, as in ``test_dropin_reference.py``) and must pass; the
@@ -29,7 +30,10 @@ SELECTIONS = [
     ("test_signal_recover_functional.py", "TestLMS", 16, ("train", "apply", "decide")),
 ]
 if os.environ.get("QB_REF_SUITE_FULL") == "1":
-    SELECTIONS.append(("test_signal_recover_functional.py", "TestDualMode or test_pol_rot", 40, ("train", "apply", "bps")))
+    # (TestDualMode::test_pmd_phase -- laser phase noise in front of a phase-locking first stage -- fails on the
+    # UNPATCHED reference for all eight of its parameter sets with the plugin's seed, and for two of them patched)
+    SELECTIONS.append(("test_signal_recover_functional.py", "(TestDualMode and not test_pmd_phase) or test_pol_rot", 30,
+                       ("train", "apply")))
 
 
 @pytest.mark.timeout(1200)
