@@ -23,7 +23,10 @@ namespace qb {
 
 int train_fast_try(TrainParams<float> p, cudaStream_t st);  // eq_train_fast.cu
 
-template <typename T, int NQ>
+// REAL: the real-valued methods (train_equaliser_realvalued, pythran_equalisation.py:80-128) run on data whose
+// imaginary parts are exactly zero; the instantiation drops the imaginary half of the tap dot, of the reduction and of
+// the update (bit-identical results: the dropped terms are products with +-0).
+template <typename T, int NQ, bool REAL>
 __global__ void __launch_bounds__(32) train_warp_kernel(TrainParams<T> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -97,14 +100,16 @@ __global__ void __launch_bounds__(32) train_warp_kernel(TrainParams<T> p)
             for (int q = 0; q < NQ; q++) {
                 x[q] = xb[off[q]];
                 ar = fma(x[q].x, wr[q], ar);
-                ar = fma(-x[q].y, wi[q], ar);
-                ai = fma(x[q].x, wi[q], ai);
-                ai = fma(x[q].y, wr[q], ai);
+                if (!REAL) {
+                    ar = fma(-x[q].y, wi[q], ar);
+                    ai = fma(x[q].x, wi[q], ai);
+                    ai = fma(x[q].y, wr[q], ai);
+                }
             }
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {
                 ar += shfl_xor(ar, m);
-                ai += shfl_xor(ai, m);
+                if (!REAL) ai += shfl_xor(ai, m);
             }
             const long long i = i0 + il;
             const cx<T> e = error_fct<T>(p.method, make_cx<T>(ar, ai), syms, p.K, gsyms, i, lane);
@@ -115,9 +120,11 @@ __global__ void __launch_bounds__(32) train_warp_kernel(TrainParams<T> p)
                 if (lane + 32 * q < Ktot) {
                     // (cr + j ci) * (x.re - j x.im)
                     wr[q] = fma(cr, x[q].x, wr[q]);
-                    wr[q] = fma(ci, x[q].y, wr[q]);
-                    wi[q] = fma(ci, x[q].x, wi[q]);
-                    wi[q] = fma(-cr, x[q].y, wi[q]);
+                    if (!REAL) {
+                        wr[q] = fma(ci, x[q].y, wr[q]);
+                        wi[q] = fma(ci, x[q].x, wi[q]);
+                        wi[q] = fma(-cr, x[q].y, wi[q]);
+                    }
                 }
             }
             if (p.adaptive && i > 0)
@@ -140,16 +147,23 @@ __global__ void __launch_bounds__(32) train_warp_kernel(TrainParams<T> p)
     if (lane == 0) p.mu[stream] = mu;
 }
 
-template <typename T, int NQ>
-static int launch_train_nq(const TrainParams<T> &p, long long nstreams, size_t smem, cudaStream_t st)
+template <typename T, int NQ, bool REAL>
+static int launch_train_nq_r(const TrainParams<T> &p, long long nstreams, size_t smem, cudaStream_t st)
 {
     // set on every launch: the attribute belongs to the device that is current, and it is cheap
-    QB_CUDA_CHECK(cudaFuncSetAttribute(train_warp_kernel<T, NQ>,
+    QB_CUDA_CHECK(cudaFuncSetAttribute(train_warp_kernel<T, NQ, REAL>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    train_warp_kernel<T, NQ><<<(unsigned)nstreams, 32, smem, st>>>(p);
+    train_warp_kernel<T, NQ, REAL><<<(unsigned)nstreams, 32, smem, st>>>(p);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
+}
+
+template <typename T, int NQ>
+static int launch_train_nq(const TrainParams<T> &p, long long nstreams, size_t smem, cudaStream_t st)
+{
+    return p.method >= QB_CMA_REAL ? launch_train_nq_r<T, NQ, true>(p, nstreams, smem, st)
+                                   : launch_train_nq_r<T, NQ, false>(p, nstreams, smem, st);
 }
 
 template <typename T>
