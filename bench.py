@@ -463,6 +463,39 @@ def dropin_records(dev):
                         "methods": list(methods), "adaptive": list(adaptive), "gpu_s": min(tg), "cpu_s": tc,
                         "speedup": tc / min(tg),
                         "rms_diff": float(np.sqrt(np.mean(np.abs(rg[0] - rc[0]) ** 2)))})
+    # BASELINE configs C2 and C3 in the reference's literal call shape: ONE capture, one stream per mode, equaliser + bps
+    from qampy_b200 import phaserecovery as ph, theory
+    for name, M, nsym, ntaps, mu, methods, A, N in (("C2 one capture", 16, 10 ** 6, 21, (1e-3,), ("mcma",), 32, 21),
+                                                    ("C3 one capture", 64, 10 ** 7, 45, (1e-3, 1e-3), ("mcma", "mrde"), 64, 45)):
+        E = synth.synth_signal(M, nsym, seed=5, snr_db=28.0, device=dev)[0].cpu().numpy()
+        al = theory.normalised_symbols(M).astype(np.complex64)
+
+        def gpu():
+            if len(methods) == 1:
+                Eo = eq.equalise_signal(E, 2, mu[0], M, Ntaps=ntaps, method=methods[0], apply=True)[0]
+            else:
+                Eo = eq.dual_mode_equalisation(E, 2, mu, M, Ntaps=ntaps, methods=methods)[0]
+            return ph.bps(Eo, A, al, N)[0]
+
+        def cpu():
+            if len(methods) == 1:
+                Eo = co.equalise_signal(E, 2, mu[0], M, Ntaps=ntaps, method=methods[0], apply=True, kind="fast_native")[0]
+            else:
+                Eo = co.dual_mode_equalisation(E, 2, mu, M, Ntaps=ntaps, methods=methods, kind="fast_native")[0]
+            return co.bps_driver(Eo, A, al, N, kind="fast_native")[0]
+        tg = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rg = gpu()
+            torch.cuda.synchronize()
+            tg.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        rc = cpu()
+        tc = time.perf_counter() - t0
+        out.append({"script": name + " (equaliser + bps, host arrays in and out)", "dtype": "complex64", "symbols": nsym,
+                    "ntaps": ntaps, "methods": list(methods), "bps": [A, N], "gpu_s": min(tg), "cpu_s": tc,
+                    "speedup": tc / min(tg), "rms_diff": float(np.sqrt(np.mean(np.abs(rg - rc) ** 2)))})
     return out
 
 
