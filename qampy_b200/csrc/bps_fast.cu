@@ -24,11 +24,30 @@
 //     consumes a packed product is a scalar add.rn (checked in SASS: the kernel contains no FFMA2).
 //   * the tail (arg-min combine across warps, unwrap, phase output, rotation) runs once per 32 rows
 //     with lane = row, on the warps of the CTA in turn so that none of them falls behind.
+//
+// Few streams (the reference's own call: bps on ONE capture, one stream per polarisation): the time of the call is the
+// serial depth of a stream, 100 cycles per row in the fused mapping above because the lane that owns a column also
+// evaluates its distances.  bps_fast_kernel<NW, NPG > 0> splits the two: NPG * NW PRODUCER warps evaluate the distances
+// of a 32-row tile (lane = angle column, warp = a quarter of the rows) into a double-buffered tile in shared memory,
+// the NW CHAIN warps only add, difference and reduce (one load replaces the 19-instruction evaluation); named barriers
+// hand the tiles over.  Same operations on the same operands in the same order per (row, angle), so indices and phases
+// are bit-identical to the fused mapping, which lets the launcher pick by the number of streams.
 #include <stdlib.h>
 
 #include "qb_common.cuh"
 
 namespace qb {
+
+template <int ID>
+__device__ __forceinline__ void fbar_sync(int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void fbar_arrive(int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
 
 struct BpsFastParams {
     const float2 *E;
@@ -114,12 +133,15 @@ constexpr int FAST_TR = 32;   // rows per tile (= lanes of the tail)
 #endif
 constexpr int FAST_NR = QB_BPS_NR;   // rows per group (independent distance evaluations in flight per lane)
 
-template <int NW>
-__global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
+// NPG: producer row groups (0: fused mapping, every chain lane evaluates its own distances)
+template <int NW, int NPG = 0>
+__global__ void __launch_bounds__(32 * NW * (1 + NPG)) bps_fast_kernel(BpsFastParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NT = 32 * NW;
+    constexpr int NT = 32 * NW * (1 + NPG);       // all threads of the CTA
+    constexpr int NC = 32 * NW;                   // chain threads
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_CHAIN = 5;   // named barriers (0 is __syncthreads)
     const int N = p.N, W = 2 * p.N;
     const long long L = p.L;
     const unsigned FULL = 0xffffffffu;
@@ -132,6 +154,8 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     float *angs = reinterpret_cast<float *>(part + 2 * NW * FAST_TR);      // [A]
     float *ust = angs + p.A;                                               // [2] unwrap state (cum, p4prev)
     float *ring = ust + 2;                                                 // [NW][W][32] running sums
+    // NPG > 0: [2][32 rows][A] distances, 16-byte aligned (also the bounce buffer of the column constants below)
+    float *dbuf = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ring + (size_t)NW * W * 32) + 15) & ~(uintptr_t)15);
 
     const float2 *E = p.E + (long long)blockIdx.x * p.stream_stride;
     int32_t *idx = p.idx ? p.idx + (long long)blockIdx.x * L : nullptr;
@@ -143,8 +167,9 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     for (int c = tid; c < p.n_im; c += NT)
         tabim[c] = make_float2(-p.lev_im[c], -p.lev_im[min(c + 1, p.n_im - 1)]);
     for (int c = tid; c < p.A; c += NT) angs[c] = p.angles ? p.angles[c] : 0.f;
-    float *ring_w = ring + (size_t)warp * W * 32;
-    for (int c = lane; c < W * 32; c += 32) ring_w[c] = 0.f;   // slot 0 = csum[0] = 0 (pythran_dsp.py:28)
+    float *ring_w = ring + (size_t)(warp < NW ? warp : 0) * W * 32;
+    if (warp < NW)
+        for (int c = lane; c < W * 32; c += 32) ring_w[c] = 0.f;   // slot 0 = csum[0] = 0 (pythran_dsp.py:28)
     FastAxis gre = make_fast_axis(p.lev_re, p.n_re, smem_u32(tabre));
     FastAxis gim = make_fast_axis(p.lev_im, p.n_im, smem_u32(tabim));
     // bounce the address constants through shared memory: ptxas otherwise splits (bits(w) << 3) + kaddr
@@ -175,25 +200,66 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     }
 
     // ---- this lane's angle column ------------------------------------------------------------------
-    const float2 cc = p.comp[warp * 32 + lane];
+    const int colw = warp % NW;                    // angle block of this warp (chain warp w and its producers)
+    const float2 cc = p.comp[colw * 32 + lane];
     // e.x * (cr, ci) and e.y * (-ci, cr) (negation commutes with rounding).  Both constants are read back
     // from shared memory as 64-bit values: a pair that ptxas can re-derive from cc is re-packed with
     // MOV + FADD in every group of the inner loop.
     f32x2 c1, c2;
     {
-        float4 *bounce = reinterpret_cast<float4 *>(part) + tid;   // part[] is not in use yet
+        // part[] is not in use yet (NPG > 0: the distance tile, which is large enough for every thread of the CTA)
+        float4 *bounce = reinterpret_cast<float4 *>(NPG > 0 ? (void *)dbuf : (void *)part) + tid;
         *bounce = make_float4(cc.x, cc.y, -cc.y, cc.x);
         asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c1), "=l"(c2) : "r"(smem_u32(bounce)) : "memory");
         __syncthreads();
     }
     float csum = 0.f;
     const uint32_t ring_lo = smem_u32(ring_w) + 4u * lane;
-    const uint32_t stage_addr = smem_u32(stage + warp * FAST_TR);
+    const uint32_t stage_addr = smem_u32(stage + (warp < NW ? warp : 0) * FAST_TR);
+    uint32_t dtile_addr = 0;                        // NPG > 0: this lane's column of the current distance tile
     float cum = 0.f, p4prev = 0.f;                  // unwrap state (NW == 1: registers; else via ust[])
 
     const long long ntiles = (L + FAST_TR - 1) / FAST_TR;
     float2 enext = lane < L ? E[lane] : make_float2(0.f, 0.f);
     uint2 mine = make_uint2(0xffffffffu, 0u);       // (min bits, ballot) of tile row `lane`
+
+    // distance of one row to the nearest alphabet point after rotation by this lane's test angle
+    auto dist = [&](float2 ev) {
+        const float2 pa = mul2_bcast(ev.x, c1), pb = mul2_bcast(ev.y, c2);
+        const float tr = __fadd_rn(pa.x, pb.x);     // E[i]*comp[a], unfused (pythran_dsp.py:79)
+        const float ti = __fadd_rn(pa.y, pb.y);
+        float2 dm;
+        dm.x = axis_min_fast(tr, gre);
+        dm.y = axis_min_fast(ti, gim);
+        const float2 sq = sqr2(dm);
+        return fminf(__fadd_rn(sq.x, sq.y), 100.f);                     // :73, :81-82 (NaN -> 100)
+    };
+
+    if (NPG > 0 && warp >= NW) {
+        // =========================== producers: distances of tile m into buffer m & 1 ===========================
+        const int pg = (warp - NW) / NW;            // this warp's rows of a tile: pg, pg + NPG, ...
+        constexpr int RPW = FAST_TR / (NPG > 0 ? NPG : 1);
+        for (long long m = 0; m < ntiles; m++) {
+            const long long i0 = m * FAST_TR;
+            float2 ev[RPW];
+#pragma unroll
+            for (int k = 0; k < RPW; k++) {
+                const long long i = i0 + pg + (long long)k * NPG;
+                ev[k] = i < L ? __ldg(E + i) : make_float2(0.f, 0.f);   // rows past the end: masked in the tail
+            }
+            if (m >= 2) {                           // the chain has finished with tile m - 2: its buffer is free
+                if (m & 1) fbar_sync<BAR_EMPTY + 1>(NT);
+                else fbar_sync<BAR_EMPTY>(NT);
+            }
+            float *dst = dbuf + (size_t)(m & 1) * FAST_TR * p.A + colw * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < RPW; k++) dst[(pg + k * NPG) * p.A] = dist(ev[k]);
+            __syncwarp();
+            if (m & 1) fbar_arrive<BAR_FULL + 1>(NT);
+            else fbar_arrive<BAR_FULL>(NT);
+        }
+        return;
+    }
 
     // FAST_NR consecutive rows of this lane's column: distance -> running sum -> window difference -> warp
     // arg-min record.  The distance evaluations are independent (ILP); only the running sum chains.
@@ -201,29 +267,33 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     // groups start at even slots, so a pair never straddles the wrap.  Shared-memory accesses are volatile
     // asm in exactly the order wanted: the input rows, the old sums, the new sums.
     auto group = [&](bool first, int rbase, const uint32_t (&aP)[FAST_NR / 2]) {
-        float2 e[FAST_NR];
         float old[FAST_NR], c[FAST_NR];
+        if (NPG == 0) {
+            float2 e[FAST_NR];
 #pragma unroll
-        for (int k = 0; k < FAST_NR / 2; k++)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(e[2 * k].x), "=f"(e[2 * k].y), "=f"(e[2 * k + 1].x), "=f"(e[2 * k + 1].y)
-                         : "r"(stage_addr + 8u * rbase + 16u * k));
-        // csum[i - 2N] (0 while i < 2N: unused)
+            for (int k = 0; k < FAST_NR / 2; k++)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(e[2 * k].x), "=f"(e[2 * k].y), "=f"(e[2 * k + 1].x), "=f"(e[2 * k + 1].y)
+                             : "r"(stage_addr + 8u * rbase + 16u * k));
+            // csum[i - 2N] (0 while i < 2N: unused)
 #pragma unroll
-        for (int k = 0; k < FAST_NR / 2; k++) {
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[2 * k]) : "r"(aP[k]));
-            asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[2 * k + 1]) : "r"(aP[k]));
-        }
+            for (int k = 0; k < FAST_NR / 2; k++) {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[2 * k]) : "r"(aP[k]));
+                asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[2 * k + 1]) : "r"(aP[k]));
+            }
 #pragma unroll
-        for (int u = 0; u < FAST_NR; u++) {
-            const float2 pa = mul2_bcast(e[u].x, c1), pb = mul2_bcast(e[u].y, c2);
-            const float tr = __fadd_rn(pa.x, pb.x);     // E[i]*comp[a], unfused (pythran_dsp.py:79)
-            const float ti = __fadd_rn(pa.y, pb.y);
-            float2 dm;
-            dm.x = axis_min_fast(tr, gre);
-            dm.y = axis_min_fast(ti, gim);
-            const float2 sq = sqr2(dm);
-            c[u] = fminf(__fadd_rn(sq.x, sq.y), 100.f);                 // :73, :81-82 (NaN -> 100)
+            for (int u = 0; u < FAST_NR; u++) c[u] = dist(e[u]);
+        } else {
+            // the producers have evaluated the distances: one load per row
+            const uint32_t da = dtile_addr + 4u * (uint32_t)p.A * (uint32_t)rbase;
+#pragma unroll
+            for (int u = 0; u < FAST_NR; u++)
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c[u]) : "r"(da + 4u * (uint32_t)p.A * u));
+#pragma unroll
+            for (int k = 0; k < FAST_NR / 2; k++) {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[2 * k]) : "r"(aP[k]));
+                asm volatile("ld.shared.f32 %0, [%1+128];" : "=f"(old[2 * k + 1]) : "r"(aP[k]));
+            }
         }
         if (first) c[0] = 0.f;                                          // row 0 is never added (:30)
 #pragma unroll
@@ -266,11 +336,17 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     for (long long m = 0; m < ntiles; m++) {
         const long long i0 = m * FAST_TR;
         const int nrows = (int)min((long long)FAST_TR, L - i0);
-        __syncwarp();
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_addr + 8u * lane), "f"(enext.x), "f"(enext.y)
-                     : "memory");
-        __syncwarp();
-        if (i0 + FAST_TR + lane < L) enext = E[i0 + FAST_TR + lane];
+        if (NPG == 0) {
+            __syncwarp();
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_addr + 8u * lane), "f"(enext.x), "f"(enext.y)
+                         : "memory");
+            __syncwarp();
+            if (i0 + FAST_TR + lane < L) enext = E[i0 + FAST_TR + lane];
+        } else {
+            if (m & 1) fbar_sync<BAR_FULL + 1>(NT);     // the distances of tile m are in buffer m & 1
+            else fbar_sync<BAR_FULL>(NT);
+            dtile_addr = smem_u32(dbuf + (size_t)(m & 1) * FAST_TR * p.A + colw * 32 + lane);
+        }
 
         // rows past the end of the stream (last group only) run on stale inputs: they come after every
         // valid row in the running sums and are masked in the tail
@@ -282,13 +358,18 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
             if (slot >= W) slot -= W;
         }
         __syncwarp();
+        if (NPG > 0) {                                  // the producers may refill this buffer (tile m + 2)
+            if (m & 1) fbar_arrive<BAR_EMPTY + 1>(NT);
+            else fbar_arrive<BAR_EMPTY>(NT);
+        }
 
         // ---- hand the 32 row records to the tail owner ----------------------------------------------
         const int owner = (int)(m % NW);
         uint2 *pbuf = part + (size_t)(m & 1) * NW * FAST_TR;
         if (NW > 1) {
             if (warp != owner) pbuf[warp * FAST_TR + lane] = mine;
-            __syncthreads();
+            if (NPG > 0) fbar_sync<BAR_CHAIN>(NC);      // chain warps only: the producers are elsewhere
+            else __syncthreads();
         }
         if (warp == owner) {
             // tail, lane = row: row i = i0 + lane with i >= 2N produces output j = i - N
@@ -348,19 +429,28 @@ __global__ void __launch_bounds__(32 * NW) bps_fast_kernel(BpsFastParams p)
     }
 }
 
-static size_t fast_smem_bytes(int NW, int A, int n_re, int n_im, int N)
+static size_t fast_smem_bytes(int NW, int A, int n_re, int n_im, int N, int npg)
 {
     return (size_t)(n_re + n_im) * 8 + (size_t)NW * FAST_TR * 8 * 3 + (size_t)A * 4 + 8 +
-           (size_t)NW * 2 * N * 32 * 4;
+           (size_t)NW * 2 * N * 32 * 4 + (npg > 0 ? (size_t)2 * FAST_TR * A * 4 + 16 : 0);
 }
 
+constexpr int FAST_NPG = 4;   // producer row groups of the few-streams mapping: 4 * NW producer warps per CTA
+
 template <int NW>
-static int launch_fast(const BpsFastParams &p, int64_t nstream, size_t smem, cudaStream_t st)
+static int launch_fast(const BpsFastParams &p, int64_t nstream, bool split, cudaStream_t st)
 {
+    const size_t smem = fast_smem_bytes(NW, p.A, p.n_re, p.n_im, p.N, split ? FAST_NPG : 0);
     // set on every launch: the attribute belongs to the device that is current, and it is cheap
-    QB_CUDA_CHECK(cudaFuncSetAttribute(bps_fast_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
-    bps_fast_kernel<NW><<<(unsigned)nstream, 32 * NW, smem, st>>>(p);
+    if (split) {
+        QB_CUDA_CHECK(cudaFuncSetAttribute(bps_fast_kernel<NW, FAST_NPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+        bps_fast_kernel<NW, FAST_NPG><<<(unsigned)nstream, 32 * NW * (1 + FAST_NPG), smem, st>>>(p);
+    } else {
+        QB_CUDA_CHECK(cudaFuncSetAttribute(bps_fast_kernel<NW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+        bps_fast_kernel<NW, 0><<<(unsigned)nstream, 32 * NW, smem, st>>>(p);
+    }
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
@@ -374,8 +464,11 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
 {
     if (n_re < 1 || n_im < 1 || A % 32 != 0 || A > 128 || 2 * N < FAST_NR) return 1;   // a group must fit the ring
     const int NW = (int)(A / 32);
-    const size_t smem = fast_smem_bytes(NW, (int)A, (int)n_re, (int)n_im, (int)N);
-    if (smem > 100 * 1024) return 1;
+    if (fast_smem_bytes(NW, (int)A, (int)n_re, (int)n_im, (int)N, FAST_NPG) > 100 * 1024) return 1;
+    // Few streams: a call lasts as long as one stream is deep -> producer / chain split (bit-identical results, so the
+    // choice may follow the launch size).  QB_BPS_SPLIT=0 / 1 forces a mapping (tests run both).
+    bool split = nstream <= 148 && A <= 64;      // at most one CTA per SM; 2 chain + 8 producer warps at A = 64
+    if (const char *e = getenv("QB_BPS_SPLIT")) split = e[0] == '1' && A <= 64;
     BpsFastParams p;
     p.E = (const float2 *)E;
     p.comp = (const float2 *)comp;
@@ -392,10 +485,10 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
     p.n_im = (int)n_im;
     p.N = (int)N;
     switch (NW) {
-    case 1: return launch_fast<1>(p, nstream, smem, st);
-    case 2: return launch_fast<2>(p, nstream, smem, st);
-    case 3: return launch_fast<3>(p, nstream, smem, st);
-    default: return launch_fast<4>(p, nstream, smem, st);
+    case 1: return launch_fast<1>(p, nstream, split, st);
+    case 2: return launch_fast<2>(p, nstream, split, st);
+    case 3: return launch_fast<3>(p, nstream, false, st);
+    default: return launch_fast<4>(p, nstream, false, st);
     }
 }
 

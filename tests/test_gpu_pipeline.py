@@ -157,12 +157,15 @@ def test_apply_batched_generic_and_fast(env):
     assert rms(out.cpu().numpy() - env.co.apply_segments(E[None], 2, w)) < 1e-13
 
 
-@pytest.fixture(params=["fast", "ws", "simple"])
+@pytest.fixture(params=["fast", "fast-split", "ws", "simple"])
 def bps_kernel(request, monkeypatch):
     """All BPS kernels: column-per-lane (default where it applies: c64, rectangular alphabet, A a multiple
-    of 32), warp-specialised tiles, phase-by-phase tiles."""
-    if request.param == "fast":
+    of 32) in its fused mapping and in the producer / chain split it takes for few streams, warp-specialised tiles,
+    phase-by-phase tiles."""
+    monkeypatch.delenv("QB_BPS_SPLIT", raising=False)
+    if request.param.startswith("fast"):
         monkeypatch.delenv("QB_BPS_KERNEL", raising=False)
+        monkeypatch.setenv("QB_BPS_SPLIT", "1" if request.param == "fast-split" else "0")
     else:
         monkeypatch.setenv("QB_BPS_KERNEL", request.param)
     return request.param
