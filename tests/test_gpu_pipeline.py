@@ -548,3 +548,39 @@ def test_bps_windowed_accumulation_follows_the_double_precision_reference(env):
     tabs128 = env.device.BpsTables(A, al, np.complex128, env.dev)
     _, _, w128 = env.device.bps(t.from_numpy(x.astype(np.complex128)).to(env.dev)[None], tabs128, N, accum="windowed")
     assert np.mean(w128.cpu().numpy()[0][N:L - N] != idx128[N:L - N]) < 1e-4
+
+
+def test_full_size_c3_warm_recipe_meets_the_reference_error_bar(env):
+    """The bench recipe at full size (BASELINE config C3: 1e7 symbols of dual-pol 64-QAM, 1183 segments): taps acquired
+    on 2 x 2^18 symbols, every segment warm-started with a phase-search halo, a second capture of the same link started
+    from the carried taps.  Symbol error rate over ALL segments after BPS below the reference's own acceptance bar
+    (ser < 1e-5, test/test_equalisation.py:92-98); a cold-started run of the same segments does not meet it."""
+    t = env.torch
+    M, nsym, S = 64, 10 ** 7, 8454
+    cfg = env.pipeline.ReceiverConfig(M=M, ntaps=45, seg_symbols=S, bps_angles=64, bps_N=45, bps_halo=45, want_err=True)
+    rx = env.pipeline.SegmentedReceiver(cfg, env.dev)
+    rx.want_idx = False
+    E1, s1 = env.synth.synth_signal(M, nsym, seed=1000, snr_db=28.0, device=env.dev)
+    taps = rx.acquire(E1)
+
+    def ser_of(res, syms):
+        errs = cmpd = 0
+        for g in res:
+            firsts = g["first"] + t.arange(g["nseg"], device=env.dev) * g["nsym"]
+            e, c = env.synth.ser_segments(g["out"], syms, M, firsts)
+            errs, cmpd = errs + int(e.sum()), cmpd + int(c.sum())
+        return errs / cmpd, cmpd
+
+    res = rx.run(E1, wxy0=taps)
+    ser1, n1 = ser_of(res, s1)
+    assert n1 > 1.99e7 and ser1 < 1e-5, ser1
+    carry = rx.carry_taps(res).clone()
+    del res
+    E2, s2 = env.synth.synth_signal(M, nsym, seed=6000, snr_db=28.0, device=env.dev)
+    res2 = rx.run(E2, wxy0=carry)
+    ser2, _ = ser_of(res2, s2)
+    assert ser2 < 1e-5, ser2
+    del res2
+    cold, _ = ser_of(rx.run(E2), s2)
+    assert cold > 1e-4, cold                      # centre-spike taps on 8454-symbol segments: not converged
+    print("C3 warm %.1e / %.1e, cold %.1e" % (ser1, ser2, cold))
