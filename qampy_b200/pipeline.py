@@ -150,6 +150,7 @@ class SegmentedReceiver:
         self._streams = None
         self.events = None      # set to a list to collect (name, (start, end)) CUDA events per launch
         self.want_idx = True
+        self.event_pool = None  # optional list of pre-created timing events for _tic
         self._nvtx_open = False
 
     def _tic(self, name):
@@ -160,7 +161,11 @@ class SegmentedReceiver:
         torch.cuda.nvtx.range_push("qampy_b200." + name)
         self._nvtx_open = True
         if self.events is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            # events from a pool made before the timed region where there is one (bench.py): creating them costs a
+            # driver call each
+            pool = self.event_pool
+            ev = (pool.pop(), pool.pop()) if pool is not None and len(pool) >= 2 else \
+                (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
             self.events.append((name, ev))
             return ev[1]
