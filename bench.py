@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays of the step")
     ap.add_argument("--no-dropin", action="store_true", help="skip the single-capture drop-in records (script shapes)")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record (one 1e9-sample capture over the ranks)")
     ap.add_argument("--no-taper", action="store_true", help="e2e path: do not cut the last chunk into 1/2 + 1/4 + 1/4")
@@ -560,29 +561,75 @@ def run_b200(a, rank, local_rank, world):
         res, taps = step(i, taps)
     del res
 
-    launches0 = _lib.launch_count()
-    rx.events = []
-    rx.event_pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * 8 * (a.steps + 1))]
-    sampler = ClockSampler(local_rank)
-    # the launches of a step are enqueued by this Python thread: a garbage-collection pause in the middle of a
-    # 90 ms timed region would be measured as GPU time
+    # The timed steps are CUDA-graph replays (one graph per capture: both trainings, FIR, BPS of the main and the
+    # end-aligned group, the hand-over of the carried taps) unless --no-graph: one launch per step instead of ~40
+    # host-side enqueues, so a descheduled Python thread cannot leave the GPU idle inside a 90 ms timed region.  The
+    # per-stage events are external event-record nodes of the graph: they hold the stage times of the last replay.
     import gc
+    graphs = None
+    launches_per_step = None
+    if not a.no_graph:
+        try:
+            taps_static = taps.clone() if taps is not None else None
+            graphs = []
+            torch.cuda.synchronize()
+            for k in range(len(caps)):
+                g = torch.cuda.CUDAGraph()
+                rx.events = []
+                l0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    E = caps[k][0]
+                    wx = rx.acquire(E) if a.start == "acquire" else taps_static
+                    res_k = rx.run(E, wxy0=wx)
+                    if a.start == "stream":
+                        taps_static.copy_(rx.carry_taps(res_k))
+                launches_per_step = _lib.launch_count() - l0
+                graphs.append((g, res_k, rx.events))
+                rx.events = None
+            for k in range(len(graphs)):          # untimed replays (graph upload)
+                graphs[k][0].replay()
+            torch.cuda.synchronize()
+        except Exception as exc:
+            sys.stderr.write("bench: CUDA graph capture failed (%r); timing eager launches\n" % (exc,))
+            graphs = None
+            rx.events = None
+            torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    if graphs is None:
+        rx.events = []
+        rx.event_pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * 8 * (a.steps + 1))]
+    sampler = ClockSampler(local_rank)
+    # (eager launches are enqueued by this Python thread: a garbage-collection pause in the middle of the timed
+    # region would be measured as GPU time)
     gc.collect()
     gc.disable()
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(a.steps):
-        res, taps = step(a.warmup + i, taps)
+    if graphs is None:
+        for i in range(a.steps):
+            res, taps = step(a.warmup + i, taps)
+    else:
+        for i in range(a.steps):
+            graphs[(a.warmup + i) % len(graphs)][0].replay()
     e1.record()
     barrier()
     gc.enable()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
-    events, rx.events = rx.events, None
-    rx.event_pool = None
+    if graphs is None:
+        launches = _lib.launch_count() - launches0
+        events, rx.events = rx.events, None
+        rx.event_pool = None
+        nsamples = a.steps
+    else:
+        last = (a.warmup + a.steps - 1) % len(graphs)
+        res, events = graphs[last][1], graphs[last][2]
+        launches = launches_per_step * a.steps
+        nsamples = 1                               # the external events hold the last replay of that graph
+        if a.start == "stream":
+            taps = taps_static
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -624,7 +671,7 @@ def run_b200(a, rank, local_rank, world):
         per.setdefault(name, []).append(s.elapsed_time(e))
     # roofline of the dominant kernel = the stage with the largest device time per step.  Algorithmic
     # bytes per symbol period: train 48 B per pass (32 B without err), apply 48 B, bps 40 B.
-    stage_ms = {k: sum(v) / a.steps for k, v in per.items()}
+    stage_ms = {k: sum(v) / nsamples for k, v in per.items()}
     bytes_train = BYTES_TRAIN if cfg.want_err else BYTES_TRAIN - 16
     stage_bytes = {"train": bytes_train * nsym_out * len(cfg.methods), "apply": BYTES_APPLY * nsym_out,
                    "bps": BYTES_BPS * nsym_out,
@@ -743,7 +790,9 @@ def run_b200(a, rank, local_rank, world):
                 "scaling": "weak" if a.workload == "c3" else "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
                 "clocks": clocks, "e2e": e2e if ok else None, "gpu_launches": int(launches), "roofline": roofline,
-                "msymbols_per_s": value / 2, "sanity": sanity}
+                "msymbols_per_s": value / 2, "sanity": sanity,
+                "timed_steps": "CUDA-graph replays of the step (one graph per capture; stage times = last replay)"
+                               if graphs is not None else "eager launches"}
         if not ok:
             line["rejected"] = "symbol error rate %.2e of the recovered symbols is not below 1e-5: the number is withheld" % ser_all
             line["withheld"] = {"value": value, "e2e": e2e}

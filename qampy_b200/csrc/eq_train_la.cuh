@@ -448,6 +448,12 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     const int B = nq / 2 + 2;
     g.tile_syms = (128 / B) * B;              // per-tile costs (loader set-up, window preload) amortised over 128 symbols
     g.pitch = 2 * (g.tile_syms + 1) + g.lpp * nq;
+    // Bank placement of the window loads (ld.shared.b64, one pair per lane): the lanes of a lane group that read input
+    // polarisation k sit k * 2 * pitch floats apart, on top of their nq-float tap stride.  With 2 * pitch = 16 (mod 32)
+    // the second polarisation's lanes fall into the banks the first one leaves free ({0, 12, 24, 4} + 16 for nq = 12,
+    // {0, 6, 12, 18} + 16 for nq = 6); the un-padded 2 * pitch = 4 (mod 32) put lane (k=1, 0) on lane (k=0, 3)'s banks:
+    // 32 % of the kernel's shared-memory wavefronts were conflict replays (profiles/r01_ncu_full_summary.txt).
+    if (LPS == 8 && p.nmodes == 2) g.pitch += (8 - (g.pitch & 15)) & 15;
     g.nslots = (GPW % p.nsel == 0) ? GPW / p.nsel : (GPW / p.nsel + 2 < GPW ? GPW / p.nsel + 2 : GPW);
     if (g.nslots < 1) g.nslots = 1;
     if (2 * g.tile_syms + g.lpp * nq + 2 > 32 * GRAM_CH) return 0;

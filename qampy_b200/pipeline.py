@@ -164,8 +164,13 @@ class SegmentedReceiver:
             # events from a pool made before the timed region where there is one (bench.py): creating them costs a
             # driver call each
             pool = self.event_pool
-            ev = (pool.pop(), pool.pop()) if pool is not None and len(pool) >= 2 else \
-                (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            if torch.cuda.is_current_stream_capturing():
+                # inside a CUDA graph: external event-record nodes, re-recorded by every replay
+                ev = (torch.cuda.Event(enable_timing=True, external=True),
+                      torch.cuda.Event(enable_timing=True, external=True))
+            else:
+                ev = (pool.pop(), pool.pop()) if pool is not None and len(pool) >= 2 else \
+                    (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
             self.events.append((name, ev))
             return ev[1]
@@ -264,9 +269,10 @@ class SegmentedReceiver:
                 events, self.events = self.events, None      # per-launch events only on the main stream
                 res[1] = self._run_group(E, *groups[1], wxy0, between)
                 self.events = events
-                for v in list(res[1].values()) + list(res[1]["ext"].values()):
-                    if torch.is_tensor(v):
-                        v.record_stream(main)
+                if not torch.cuda.is_current_stream_capturing():     # (a captured graph owns its memory pool)
+                    for v in list(res[1].values()) + list(res[1]["ext"].values()):
+                        if torch.is_tensor(v):
+                            v.record_stream(main)
         res[0] = self._run_group(E, *groups[0], wxy0, between)
         if len(groups) > 1:
             main.wait_stream(self.side)
