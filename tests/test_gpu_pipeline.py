@@ -584,3 +584,39 @@ def test_full_size_c3_warm_recipe_meets_the_reference_error_bar(env):
     cold, _ = ser_of(rx.run(E2), s2)
     assert cold > 1e-4, cold                      # centre-spike taps on 8454-symbol segments: not converged
     print("C3 warm %.1e / %.1e, cold %.1e" % (ser1, ser2, cold))
+
+
+def test_receiver_step_is_graph_capturable_with_stage_events(env):
+    """What bench.py times: SegmentedReceiver.run (main group + end-aligned group on a side stream, warm start, halo,
+    error arrays) and the hand-over of the carried taps captured into ONE CUDA graph; a replay on new samples in the
+    same buffers gives what the eager call gives, and the per-stage events (external event-record nodes) carry times."""
+    t = env.torch
+    M, ntaps, S = 64, 45, 2048
+    cfg = env.pipeline.ReceiverConfig(M=M, ntaps=ntaps, seg_symbols=S, bps_angles=64, bps_N=45, bps_halo=45,
+                                      want_err=True, acq_symbols=6000)
+    rx = env.pipeline.SegmentedReceiver(cfg, env.dev)
+    Ea, _ = env.synth.synth_signal(M, 21000, seed=1, snr_db=28.0, device=env.dev)
+    Eb, _ = env.synth.synth_signal(M, 21000, seed=2, snr_db=28.0, device=env.dev)
+    taps0 = rx.acquire(Ea)
+    rx.run(Ea, wxy0=taps0)                                   # warm-up outside the capture (side stream, attributes)
+    buf = Ea.clone()
+    taps_static = taps0.clone()
+    t.cuda.synchronize()
+    g = t.cuda.CUDAGraph()
+    rx.events = []
+    with t.cuda.graph(g):
+        res = rx.run(buf, wxy0=taps_static)
+        taps_static.copy_(rx.carry_taps(res))
+    events, rx.events = rx.events, None
+    assert len(res) == 2 and [n for n, _ in events] == ["train", "train", "apply", "bps"]
+    for E in (Ea, Eb):
+        buf.copy_(E)
+        taps_static.copy_(taps0)
+        g.replay()
+        t.cuda.synchronize()
+        ref = rx.run(E, wxy0=taps0)
+        for a, b in zip(res, ref):
+            assert t.equal(a["out"], b["out"]) and t.equal(a["ph"], b["ph"]) and t.equal(a["taps"], b["taps"])
+            assert t.equal(a["err"][1], b["err"][1])
+        assert t.equal(taps_static, rx.carry_taps(ref))
+        assert all(s.elapsed_time(e) > 0 for _, (s, e) in events)
