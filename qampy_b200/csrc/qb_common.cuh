@@ -63,6 +63,11 @@ __device__ __forceinline__ T shfl_xor(T v, int m)
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
 template <typename T>
+__device__ __forceinline__ T shfl_up(T v, int d)
+{
+    return __shfl_up_sync(0xffffffffu, v, d);
+}
+template <typename T>
 __device__ __forceinline__ T shfl_idx(T v, int l)
 {
     return __shfl_sync(0xffffffffu, v, l);

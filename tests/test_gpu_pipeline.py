@@ -27,7 +27,7 @@ def env():
     return ns
 
 
-@pytest.mark.parametrize("kernel", ["la8", "la32", "lps8", "lps16", "warp"])
+@pytest.mark.parametrize("kernel", ["la8", "la32", "lps8", "lps16", "warp", "gla"])
 @pytest.mark.parametrize("M,ntaps,nmodes", [(64, 45, 2), (16, 21, 2), (4, 11, 1), (16, 17, 2), (64, 64, 2)])
 def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypatch):
     """Every training kernel (look-ahead in the throughput layout and in the latency layout = one stream per warp
@@ -36,8 +36,8 @@ def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypa
     import qampy_b200.pythran_equalisation as pe
     for var in ("QB_TRAIN_KERNEL", "QB_TRAIN_LPS"):
         monkeypatch.delenv(var, raising=False)
-    if kernel == "warp":
-        monkeypatch.setenv("QB_TRAIN_KERNEL", "warp")
+    if kernel in ("warp", "gla"):                      # generic kernels: direct form, look-ahead form
+        monkeypatch.setenv("QB_TRAIN_KERNEL", kernel)
     elif kernel not in ("la8", "la32"):                # la8 = default: look-ahead form where instantiated
         monkeypatch.setenv("QB_TRAIN_LPS", kernel[3:])  # direct form, 8 or 16 lanes per stream
     E, _ = env.synth.synth_numpy(M, 5000, nmodes=nmodes, seed=M + ntaps, snr_db=24.0)
