@@ -26,6 +26,7 @@ PROTOTYPES = {
     "qb_launch_count": ([], _i64),
     "qb_set_train_layout": ([_int], _int),
     "qb_set_bps_accumulation": ([_int], _int),
+    "qb_set_option": ([ctypes.c_char_p, ctypes.c_char_p], _int),
     "qb_train_equaliser_dev": ([_int, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64,
                                 _int, _vp, _i64, _int, _vp, _vp, _vp], _int),
     "qb_train_equaliser_host": ([_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _int,

@@ -584,15 +584,15 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
                                        200 * 1024));
     if (nstream > 2147483647LL) return set_error(QB_ERR_UNSUPPORTED, "bps: too many streams");
     // default: column-per-lane kernel (bps_fast.cu) where it applies, else the warp-specialised tile kernel;
-    // QB_BPS_KERNEL=ws / simple select the tile kernels (tests run all three)
-    const char *force = getenv("QB_BPS_KERNEL");
-    if (comp_rows || p.windowed) force = "simple";   // per-symbol angle tables, windowed sums: phase-by-phase kernel only
-    if (sizeof(T) == 4 && !(force && (force[0] == 's' || force[0] == 'w'))) {
+    // option BPS_KERNEL (qb_set_option) = ws / simple selects the tile kernels (tests run all three)
+    char force = option_char(OPT_BPS_KERNEL);
+    if (comp_rows || p.windowed) force = 's';   // per-symbol angle tables, windowed sums: phase-by-phase kernel only
+    if (sizeof(T) == 4 && force != 's' && force != 'w') {
         const int rc = bps_fast_dispatch(E, nstream, stream_stride, L, comp, angles, A, lev_re, n_re, lev_im, n_im,
                                          N, idx, ph, Eout, st);
         if (rc <= 0) return rc;
     }
-    if (!(force && force[0] == 's')) {
+    if (force != 's') {
         int RRw = 64;
         while (RRw < 2 * WS_TR + W) RRw <<= 1;
         const size_t smem_ws = ((size_t)RRw * A + (size_t)A * (WS_TR + 1) + 32 + A) * sizeof(T) +

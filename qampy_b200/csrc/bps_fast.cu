@@ -466,9 +466,9 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
     const int NW = (int)(A / 32);
     if (fast_smem_bytes(NW, (int)A, (int)n_re, (int)n_im, (int)N, FAST_NPG) > 100 * 1024) return 1;
     // Few streams: a call lasts as long as one stream is deep -> producer / chain split (bit-identical results, so the
-    // choice may follow the launch size).  QB_BPS_SPLIT=0 / 1 forces a mapping (tests run both).
+    // choice may follow the launch size).  Option BPS_SPLIT = 0 / 1 (qb_set_option) forces a mapping (tests run both).
     bool split = nstream <= 148 && A <= 64;      // at most one CTA per SM; 2 chain + 8 producer warps at A = 64
-    if (const char *e = getenv("QB_BPS_SPLIT")) split = e[0] == '1' && A <= 64;
+    if (const char e = option_char(OPT_BPS_SPLIT)) split = e == '1' && A <= 64;
     BpsFastParams p;
     p.E = (const float2 *)E;
     p.comp = (const float2 *)comp;

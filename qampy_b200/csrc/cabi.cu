@@ -27,6 +27,50 @@ int set_error(int code, const char *fmt, ...)
 }
 void count_launch(int n) { g_launches += n; }
 
+// kernel-selection overrides: a small table behind a mutex, seeded once from the environment
+static const char *const OPTION_NAMES[OPT_COUNT] = {"TRAIN_KERNEL", "TRAIN_LPS", "TRAIN_GLA", "LA_TILE", "BPS_KERNEL", "BPS_SPLIT"};
+static std::mutex g_opt_mutex;
+static bool g_opt_seeded = false;
+static bool g_opt_set[OPT_COUNT];
+static char g_opt_val[OPT_COUNT][24];
+static void seed_options_locked()
+{
+    if (g_opt_seeded) return;
+    g_opt_seeded = true;
+    for (int o = 0; o < OPT_COUNT; o++) {
+        char name[48];
+        snprintf(name, sizeof(name), "QB_%s", OPTION_NAMES[o]);
+        const char *e = getenv(name);
+        g_opt_set[o] = e && e[0];
+        if (g_opt_set[o]) snprintf(g_opt_val[o], sizeof(g_opt_val[o]), "%s", e);
+    }
+}
+char option_char(Option o)
+{
+    std::lock_guard<std::mutex> lk(g_opt_mutex);
+    seed_options_locked();
+    return g_opt_set[o] ? g_opt_val[o][0] : 0;
+}
+int option_int(Option o, int unset)
+{
+    std::lock_guard<std::mutex> lk(g_opt_mutex);
+    seed_options_locked();
+    return g_opt_set[o] ? atoi(g_opt_val[o]) : unset;
+}
+static int set_option(const char *name, const char *value)
+{
+    if (!name) return set_error(QB_ERR_ARG, "qb_set_option: name is NULL");
+    std::lock_guard<std::mutex> lk(g_opt_mutex);
+    seed_options_locked();
+    for (int o = 0; o < OPT_COUNT; o++) {
+        if (strcmp(name, OPTION_NAMES[o]) != 0) continue;
+        g_opt_set[o] = value && value[0];
+        if (g_opt_set[o]) snprintf(g_opt_val[o], sizeof(g_opt_val[o]), "%s", value);
+        return QB_OK;
+    }
+    return set_error(QB_ERR_ARG, "qb_set_option: unknown option '%s'", name);
+}
+
 int set_train_layout(int layout);
 int set_bps_accumulation(int mode);
 int apply_dispatch(int dtype, const void *E, int64_t nseg, int64_t seg_stride, int64_t row_stride,
@@ -208,6 +252,7 @@ const char *qb_last_error(void) { return g_err; }
 int64_t qb_launch_count(void) { return g_launches.load(); }
 int qb_set_train_layout(int layout) { return qb::set_train_layout(layout); }
 int qb_set_bps_accumulation(int mode) { return qb::set_bps_accumulation(mode); }
+int qb_set_option(const char *name, const char *value) { return qb::set_option(name, value); }
 
 int qb_device_count(void)
 {

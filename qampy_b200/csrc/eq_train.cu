@@ -200,20 +200,19 @@ static int launch_train(const void *E, int64_t nseg, int64_t seg_stride, int64_t
     p.nstreams = nseg * nsel;
     if (p.nstreams > 2147483647LL) return set_error(QB_ERR_UNSUPPORTED, "train_equaliser: too many streams");
     if (sizeof(T) == 4) {
-        // QB_TRAIN_KERNEL=warp forces the generic warp-per-stream kernel, =gla the generic look-ahead kernel (used by
-        // the parity tests)
-        const char *force = getenv("QB_TRAIN_KERNEL");
+        // option TRAIN_KERNEL (qb_set_option) = warp forces the generic warp-per-stream kernel, = gla the generic
+        // look-ahead kernel (used by the parity tests)
+        const char force = option_char(OPT_TRAIN_KERNEL);
         // the real-valued error functions (QB_*_REAL) only exist in the generic kernels
-        if (!(force && (force[0] == 'w' || force[0] == 'g')) && method < QB_CMA_REAL) {
+        if (force != 'w' && force != 'g' && method < QB_CMA_REAL) {
             const int rc = train_fast_try(*reinterpret_cast<TrainParams<float> *>(&p), st);
             if (rc != 0) return rc < 0 ? rc : QB_OK;
         }
     }
     {
-        // generic look-ahead kernel (any dtype / os / nmodes, nmodes*ntaps <= 128); QB_TRAIN_KERNEL=warp keeps the
+        // generic look-ahead kernel (any dtype / os / nmodes, nmodes*ntaps <= 128); TRAIN_KERNEL = warp keeps the
         // direct warp-per-stream form
-        const char *force = getenv("QB_TRAIN_KERNEL");
-        if (!(force && force[0] == 'w')) {
+        if (option_char(OPT_TRAIN_KERNEL) != 'w') {
             const int rc = train_gla_try<T>(p, st);
             if (rc != 0) return rc < 0 ? rc : QB_OK;
         }

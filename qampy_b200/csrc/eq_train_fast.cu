@@ -36,16 +36,14 @@ int train_fast_try(TrainParams<float> p, cudaStream_t st)
     // (eq_train_fast.cuh, detect_grid): 32 axis levels + one byte per alphabet point
     const bool searched = p.method == QB_SBD || p.method == QB_DD || p.method == QB_MDDMA;
     p.nsym_pitch = p.nsym_smem + ((searched && p.K >= 4 && p.K <= GRID_MAX_K) ? 16 + (p.K + 7) / 8 : 0);
-    // QB_TRAIN_LPS = 8 | 16 forces a layout (tests, tuning)
-    int forced = 0;
-    if (const char *e = getenv("QB_TRAIN_LPS")) forced = atoi(e);
+    // option TRAIN_LPS = 8 | 16 (qb_set_option) forces a layout (tests, tuning)
+    const int forced = option_int(OPT_TRAIN_LPS, 0);
     // Default: 8 lanes per stream (fewest instructions per trained symbol; measured fastest from 2 to
     // thousands of streams on B200).  A fixed layout also keeps a segment's result independent of how
     // many other segments share the launch.
     // Look-ahead form of the recurrence (eq_train_la.cuh) where it is instantiated: fixed step size, 8 lanes per
-    // stream, 6 or 12 taps per lane.  QB_TRAIN_KERNEL=direct keeps the direct form (tests run both).
-    const char *kern = getenv("QB_TRAIN_KERNEL");
-    if (!forced && !(kern && kern[0] == 'd')) {
+    // stream, 6 or 12 taps per lane.  Option TRAIN_KERNEL = direct keeps the direct form (tests run both).
+    if (!forced && option_char(OPT_TRAIN_KERNEL) != 'd') {
         // The layout is the CALLER's choice, never a function of how many streams a launch holds: a stream's
         // result stays independent of what shares its launch.
         int rc = g_train_layout == 1 ? train_la_l32(p, st) : 0;

@@ -265,12 +265,11 @@ static int launch_gla_nq(const TrainParams<T> &p, size_t smem, cudaStream_t st)
 }
 
 // Returns 1 if launched, 0 if the shape is outside this kernel (caller keeps the direct form), < 0 on error.
-// QB_TRAIN_GLA=0 keeps the direct form (tests run both).
+// Option TRAIN_GLA = 0 (qb_set_option) keeps the direct form.
 template <typename T>
 int train_gla_try(TrainParams<T> p, cudaStream_t st)
 {
-    const char *e = getenv("QB_TRAIN_GLA");
-    if (e && e[0] == '0') return 0;
+    if (option_char(OPT_TRAIN_GLA) == '0') return 0;
     if (p.method >= QB_CMA_REAL) return 0;                     // real-valued methods: REAL instantiation of the direct form
     const int Ktot = p.nmodes * p.ntaps;
     const int nq = (Ktot + 31) / 32;

@@ -446,7 +446,12 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     // 2 / 4 with one stream per warp (the latency layout)
     if (LPS == 32 ? (nq != 2 && nq != 4) : (nq != 6 && nq != 12)) return 0;
     const int B = nq / 2 + 2;
-    g.tile_syms = (128 / B) * B;              // per-tile costs (loader set-up, window preload) amortised over 128 symbols
+    // per-tile costs (loader set-up, window preload) amortised over 128 symbols; option LA_TILE overrides the target
+    // for occupancy experiments: a shorter tile is a smaller shared-memory slice, so more warps fit an SM (measured:
+    // shorter tiles are slower at every occupancy, profiles/README.md)
+    const int tile_opt = option_int(OPT_LA_TILE, 0);
+    const int tile_target = tile_opt >= B ? tile_opt : 128;
+    g.tile_syms = (tile_target / B) * B;
     g.pitch = 2 * (g.tile_syms + 1) + g.lpp * nq;
     // Bank placement of the window loads (ld.shared.b64, one pair per lane): the lanes of a lane group that read input
     // polarisation k sit k * 2 * pitch floats apart, on top of their nq-float tap stride.  With 2 * pitch = 16 (mod 32)

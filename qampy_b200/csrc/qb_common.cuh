@@ -12,6 +12,14 @@ namespace qb {
 int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
 
+// ---- kernel-selection overrides (tests, tuning) -----------------------------------------------
+// Values are set through qb_set_option (include/qampy_b200.h); the environment (QB_<NAME>) is read ONCE, when the first
+// option is looked up, never per launch.  option_char: first character of the value, 0 if unset; option_int: the
+// value as an integer, `unset` if unset.
+enum Option { OPT_TRAIN_KERNEL, OPT_TRAIN_LPS, OPT_TRAIN_GLA, OPT_LA_TILE, OPT_BPS_KERNEL, OPT_BPS_SPLIT, OPT_COUNT };
+char option_char(Option o);
+int option_int(Option o, int unset);
+
 #define QB_CUDA_CHECK(expr)                                                                  \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \

@@ -37,6 +37,13 @@ def _modes_arg(modes, nmodes):
     return modes, modes.ctypes.data_as(ctypes.c_void_p)
 
 
+def set_option(name, value=None):
+    """Kernel-selection override for tests and tuning (``qb_set_option`` in the header): ``name`` without the ``QB_``
+    prefix ("TRAIN_KERNEL", "TRAIN_LPS", "TRAIN_GLA", "LA_TILE", "BPS_KERNEL", "BPS_SPLIT"); ``None`` clears it."""
+    lib = _lib.load()
+    _lib.check(lib.qb_set_option(name.encode(), None if value is None else str(value).encode()))
+
+
 def segment_view(E, nseg, seg_out_symbols, os, ntaps, step_symbols=None):
     """Overlapping time-segment view (no copy) of a capture ``E`` (nmodes, L): segment s covers the
     input samples that produce output symbols [s*seg_out_symbols, (s+1)*seg_out_symbols), i.e.

@@ -27,3 +27,22 @@ def golden():
         return cache[name]
 
     return load
+
+
+@pytest.fixture
+def qb_option():
+    """Kernel-selection overrides of the library for one test (qb_set_option in include/qampy_b200.h); everything the
+    test set is cleared afterwards."""
+    from qampy_b200 import device
+
+    touched = set()
+
+    def set_option(name, value):
+        touched.add(name)
+        device.set_option(name, value)
+
+    for name in ("TRAIN_KERNEL", "TRAIN_LPS", "BPS_KERNEL", "BPS_SPLIT"):   # nothing left over from the environment
+        set_option(name, None)
+    yield set_option
+    for name in touched:
+        device.set_option(name, None)

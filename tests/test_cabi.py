@@ -63,6 +63,16 @@ def test_detect_grid_host_helper():
                                    ctypes.byref(nim)) == 0
 
 
+def test_set_option_accepts_known_names_only():
+    """qb_set_option: the kernel-selection overrides of the tests (the environment is read once, never per launch)."""
+    lib = _lib.load()
+    for name in (b"TRAIN_KERNEL", b"TRAIN_LPS", b"TRAIN_GLA", b"LA_TILE", b"BPS_KERNEL", b"BPS_SPLIT"):
+        assert lib.qb_set_option(name, b"1") == 0
+        assert lib.qb_set_option(name, None) == 0
+    assert lib.qb_set_option(b"NO_SUCH_OPTION", b"1") == -1 and b"unknown option" in lib.qb_last_error()
+    assert lib.qb_set_option(None, None) == -1
+
+
 def test_invalid_arguments_are_rejected_with_messages():
     lib = _lib.load()
     z = ctypes.c_void_p(0)

@@ -29,17 +29,15 @@ def env():
 
 @pytest.mark.parametrize("kernel", ["la8", "la32", "lps8", "lps16", "warp", "gla"])
 @pytest.mark.parametrize("M,ntaps,nmodes", [(64, 45, 2), (16, 21, 2), (4, 11, 1), (16, 17, 2), (64, 64, 2)])
-def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, monkeypatch):
+def test_train_kernel_variants_vs_oracle(env, kernel, M, ntaps, nmodes, qb_option):
     """Every training kernel (look-ahead in the throughput layout and in the latency layout = one stream per warp
     with the fixed-point warp reduction; direct planar/packed with 8 or 16 lanes per stream; generic warp per
     stream) on 3 segments, all error functions with a dedicated code path."""
     import qampy_b200.pythran_equalisation as pe
-    for var in ("QB_TRAIN_KERNEL", "QB_TRAIN_LPS"):
-        monkeypatch.delenv(var, raising=False)
     if kernel in ("warp", "gla"):                      # generic kernels: direct form, look-ahead form
-        monkeypatch.setenv("QB_TRAIN_KERNEL", kernel)
+        qb_option("TRAIN_KERNEL", kernel)
     elif kernel not in ("la8", "la32"):                # la8 = default: look-ahead form where instantiated
-        monkeypatch.setenv("QB_TRAIN_LPS", kernel[3:])  # direct form, 8 or 16 lanes per stream
+        qb_option("TRAIN_LPS", kernel[3:])             # direct form, 8 or 16 lanes per stream
     E, _ = env.synth.synth_numpy(M, 5000, nmodes=nmodes, seed=M + ntaps, snr_db=24.0)
     t = env.torch
     nseg, S = 3, 1500
@@ -158,16 +156,14 @@ def test_apply_batched_generic_and_fast(env):
 
 
 @pytest.fixture(params=["fast", "fast-split", "ws", "simple"])
-def bps_kernel(request, monkeypatch):
+def bps_kernel(request, qb_option):
     """All BPS kernels: column-per-lane (default where it applies: c64, rectangular alphabet, A a multiple
     of 32) in its fused mapping and in the producer / chain split it takes for few streams, warp-specialised tiles,
     phase-by-phase tiles."""
-    monkeypatch.delenv("QB_BPS_SPLIT", raising=False)
     if request.param.startswith("fast"):
-        monkeypatch.delenv("QB_BPS_KERNEL", raising=False)
-        monkeypatch.setenv("QB_BPS_SPLIT", "1" if request.param == "fast-split" else "0")
+        qb_option("BPS_SPLIT", "1" if request.param == "fast-split" else "0")
     else:
-        monkeypatch.setenv("QB_BPS_KERNEL", request.param)
+        qb_option("BPS_KERNEL", request.param)
     return request.param
 
 
