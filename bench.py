@@ -51,7 +51,8 @@ def parse():
                          "per-rank ranges of whole segments (strong scaling, no collective)")
     ap.add_argument("--nsym", type=int, default=10 ** 7, help="symbols per polarisation per GPU")
     ap.add_argument("--seg", type=int, default=-1,
-                    help="output symbols per segment; -1 = smallest length >= 8192 that fills whole GPU waves "
+                    help="output symbols per segment; -1 = smallest length >= 4096 that fills whole GPU waves of two training "
+                         "warps per SM sub-partition "
                          "(pipeline.balanced_segment_symbols), 0 = one segment")
     ap.add_argument("--start", default="stream", choices=["stream", "acquire", "cold"],
                     help="what a segment's taps start from.  stream (default): the taps the receiver carries from capture "
@@ -680,8 +681,8 @@ def run_b200(a, rank, local_rank, world):
     kernels = {"train": "train_la_kernel<8,12,METHOD,2> (look-ahead eq_train; two launches per step: mcma, mrde)",
                "apply": "apply_2x2_os2_kernel", "bps": "bps_fast_kernel<2>",
                "acquire": "single-stream trainer (%s layout), one stream per mode; two launches: mcma, mrde" % a.acq_layout}
-    limits = {"train": "instruction issue of one warp per SM sub-partition (4 serial streams each; 60 flop/B at "
-                       "ntaps 45), not HBM",
+    limits = {"train": "instruction dispatch: two training warps per SM sub-partition (4 serial streams each) saturate it, "
+                       "packed fp32x2 FMAs take two dispatch cycles (60 flop/B at ntaps 45), not HBM",
               "apply": "FP32 FMA issue (30 flop/B at ntaps 45), not HBM",
               "bps": "instruction issue of the 64-angle distance search (19 instructions per symbol and angle), not HBM",
               "acquire": "serial depth of one stream (the recurrence of ONE mode is not parallel), not HBM"}
@@ -841,7 +842,9 @@ def resolve_segments(a):
                 n_sm = torch.cuda.get_device_properties(int(os.environ.get("LOCAL_RANK", "0"))).multi_processor_count
         except Exception:
             pass
-        a.seg = pipeline.balanced_segment_symbols(2 * a.nsym, cfg, target=8192, n_sm=n_sm)
+        # two training warps per SM sub-partition: from there on the trainer is bound by instruction dispatch, not by the
+        # issue cadence of a lone warp (profiles/README.md: 1 / 2 / 3 / 4 resident warps: 1.05 / 0.92 / 0.93 / 0.90 ms per pass)
+        a.seg = pipeline.balanced_segment_symbols(2 * a.nsym, cfg, target=4096, n_sm=n_sm, warps_per_sm=8)
     return a
 
 

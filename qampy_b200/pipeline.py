@@ -151,6 +151,7 @@ class SegmentedReceiver:
         self.events = None      # set to a list to collect (name, (start, end)) CUDA events per launch
         self.want_idx = True
         self.event_pool = None  # optional list of pre-created timing events for _tic
+        self.trace = None       # set to a list: run_host appends (label, timing event) per chunk and copy (scratch/e2e_trace.py)
         self._nvtx_open = False
 
     def _tic(self, name):
@@ -289,6 +290,13 @@ def _host_chunks(groups, nchunks, taper=True):
     first, nsym, nseg, drop = groups[0]
     nchunks = max(1, min(nchunks, nseg))
     bounds = [shard_segments(nseg, c, nchunks) for c in range(nchunks)]
+    if taper and nchunks > 1 and bounds[0][1] - bounds[0][0] >= 8:
+        # and the first run into 1/4 + 1/4 + 1/2: nothing can be downloaded before the first run's first training
+        # stage is done, and the download is the longer direction of the link -- the sooner it starts the better
+        lo, hi = bounds.pop(0)
+        n = hi - lo
+        cuts = [lo, lo + n // 4, lo + n // 2, hi]
+        bounds = [(cuts[i], cuts[i + 1]) for i in range(3)] + bounds
     if taper and nchunks > 1 and bounds[-1][1] - bounds[-1][0] >= 8:
         lo, hi = bounds.pop()
         n = hi - lo
@@ -331,17 +339,31 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, tap
         err_host = [torch.empty((nseg_total, nmodes, tr * cfg.niter[k]), dtype=rx.tdtype, pin_memory=True)
                     for k in range(len(cfg.methods))]
     rx.err_host = err_host if cfg.want_err else None
-    if rx._streams is None or len(rx._streams["comp"]) < min(nchunks + 3, 19):
+    if rx._streams is None or len(rx._streams["comp"]) < min(nchunks + 5, 21):
         # one compute stream per chunk: the training kernel is latency bound, so the chains of different
         # chunks must run side by side rather than queue behind each other
-        rx._streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(), d2h_err=torch.cuda.Stream(),
-                           comp=[torch.cuda.Stream() for _ in range(min(nchunks + 3, 19))])
+        # one download stream per kind of result (errors of stage k, recovered symbols): a stream is a queue in host
+        # order (chunk by chunk), and on ONE queue the first-stage errors of chunk c+1, ready long before the
+        # second-stage errors of chunk c, would wait behind them with the link idle
+        rx._streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
+                           d2h_err=[torch.cuda.Stream() for _ in range(len(cfg.methods))],
+                           comp=[torch.cuda.Stream() for _ in range(min(nchunks + 5, 21))])
     st = rx._streams
     main = torch.cuda.current_stream()
-    for s_ in [st["h2d"], st["d2h"], st["d2h_err"]] + st["comp"]:
+    all_streams = [st["h2d"], st["d2h"]] + st["d2h_err"] + st["comp"]
+    for s_ in all_streams:
         s_.wait_stream(main)
     events, rx.events = rx.events, None
     keep = []
+
+    def mark(label):
+        # optional timeline of the overlapped path (rx.trace): one timing event on the current stream
+        if rx.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            rx.trace.append((label, ev))
+
+    mark("start")
     copied_to = 0                                                   # samples [0, copied_to) are on the device
     for ci, (first, nsym, nseg, drop, seg0) in enumerate(_host_chunks(groups, nchunks, taper)):
         need = min(L, (first + nsym * nseg + H) * cfg.os + cfg.ntaps - 1)
@@ -352,6 +374,7 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, tap
                     E_dev[k, copied_to:need].copy_(E_host[k, copied_to:need], non_blocking=True)
                 copied_to = need
             ev_in.record()
+            mark("h2d %d" % ci)
         comp = st["comp"][ci % len(st["comp"])]
         ev_out = torch.cuda.Event()
         with torch.cuda.stream(comp):
@@ -364,20 +387,24 @@ def run_host(rx, E_host, out_host=None, ph_host=None, nchunks=6, E_dev=None, tap
                     return
                 ev = torch.cuda.Event()
                 ev.record()
-                with torch.cuda.stream(st["d2h_err"]):
-                    st["d2h_err"].wait_event(ev)
+                mark("train%d %d" % (stage, ci))
+                with torch.cuda.stream(st["d2h_err"][stage]):
+                    st["d2h_err"][stage].wait_event(ev)
                     err_host[stage][seg0:seg0 + nseg].copy_(err, non_blocking=True)
+                    mark("d2h err%d %d" % (stage, ci))
 
             res = rx._run_group(E_dev, first, nsym, nseg, drop, wxy0, None, stage_done if cfg.want_err else None)
             ev_out.record()
+            mark("chain %d" % ci)
         with torch.cuda.stream(st["d2h"]):
             st["d2h"].wait_event(ev_out)
             out_host[seg0:seg0 + nseg].copy_(res["ext"]["out"], non_blocking=True)
             ph_host[seg0:seg0 + nseg].copy_(res["ext"]["ph"], non_blocking=True)
+            mark("d2h out %d" % ci)
         keep.append(res)
         if drop == 0:
             rx.host_carry = res["taps"][-1]                         # taps of the last full segment (carry_taps)
-    for s_ in [st["h2d"], st["d2h"], st["d2h_err"]] + st["comp"]:
+    for s_ in all_streams:
         main.wait_stream(s_)
     rx.events = events
     rx._keep = keep                                                 # alive until the caller synchronises

@@ -190,8 +190,8 @@ def test_unique_alphabet_keeps_first_occurrences_and_decisions():
 
 
 def test_host_chunks_tile_the_segments_and_taper_the_last_run():
-    """The overlapped host path cuts the main group into runs of whole segments (last run tapered 1/2 + 1/4 + 1/4,
-    the end-aligned extra segment last): every segment exactly once, in order."""
+    """The overlapped host path cuts the main group into runs of whole segments (first run tapered 1/4 + 1/4 + 1/2,
+    last run 1/2 + 1/4 + 1/4, the end-aligned extra segment last): every segment exactly once, in order."""
     from qampy_b200 import pipeline
     for nseg, extra in ((1182, True), (1184, False), (5, True), (1, False), (40, False)):
         groups = [(0, 100, nseg, 0)] + ([(nseg * 100 - 37, 100, 1, 63)] if extra else [])
@@ -205,7 +205,8 @@ def test_host_chunks_tile_the_segments_and_taper_the_last_run():
                 if extra:
                     assert runs[-1] == (nseg * 100 - 37, 100, 1, 63, nseg)
                 if taper and nchunks > 1 and nseg // min(nchunks, nseg) >= 8:
-                    assert len(main) == min(nchunks, nseg) + 2 and main[-1][2] <= main[0][2] // 3 + 1
+                    assert len(main) == min(nchunks, nseg) + 4 and main[-1][2] <= main[3][2] // 3 + 1
+                    assert main[0][2] <= main[3][2] // 3 + 1 and main[1][2] <= main[3][2] // 3 + 1
                 else:
                     assert len(main) == min(nchunks, nseg)
 
