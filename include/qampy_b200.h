@@ -255,7 +255,7 @@ int qb_set_bps_accumulation(int mode);
 
 /* ---- kernel-selection overrides (tests and tuning only; results are the same to the parity bounds) ------
  * Process-wide.  name: "TRAIN_KERNEL" (direct | warp | gla), "TRAIN_LPS" (8 | 16), "TRAIN_GLA" (0), "LA_TILE" (symbols
- * per staged tile of the look-ahead trainer), "BPS_KERNEL" (ws | simple), "BPS_SPLIT" (0 | 1).  value NULL or "" clears
+ * per staged tile of the look-ahead trainer), "BPS_KERNEL" (ws | simple), "BPS_SPLIT" (0 | 1 | 2: fused, producer / chain, phase-parallel mapping).  value NULL or "" clears
  * the override.  Initial values come from the environment variables QB_<name>, read once at the first use, never per
  * launch.  Returns QB_OK, or QB_ERR_ARG for an unknown name.  Nothing in the reference corresponds to this.        */
 int qb_set_option(const char *name, const char *value);

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libqampy_b200.so")
 SOURCES = ["cabi.cu", "eq_apply.cu", "eq_train.cu", "eq_train_gla.cu", "eq_train_fast.cu", "eq_train_fast_l8.cu", "eq_train_fast_l8a.cu", "eq_train_fast_l8b.cu", "eq_train_fast_l8c.cu", "eq_train_fast_l16.cu", "eq_train_la_l8.cu", "eq_train_la_l8a.cu", "eq_train_la_l32.cu", "eq_train_la_l32a.cu",
-           "bps.cu", "bps_fast.cu", "pilot_ops.cu", "synth_ops.cu", "decision.cu", "vv.cu"]
+           "bps.cu", "bps_fast.cu", "bps_par.cu", "pilot_ops.cu", "synth_ops.cu", "decision.cu", "vv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 OBJDIR = os.path.join(LIBDIR, "obj")    # one object per translation unit: a change rebuilds only what includes it

@@ -34,7 +34,7 @@
 // are bit-identical to the fused mapping, which lets the launcher pick by the number of streams.
 #include <stdlib.h>
 
-#include "qb_common.cuh"
+#include "bps_dist.cuh"
 
 namespace qb {
 
@@ -49,83 +49,8 @@ __device__ __forceinline__ void fbar_arrive(int count)
     asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
 }
 
-struct BpsFastParams {
-    const float2 *E;
-    const float2 *comp;
-    const float *angles;
-    const float *lev_re, *lev_im;
-    int32_t *idx;
-    float *ph;
-    float2 *Eout;
-    long long stream_stride, L;
-    int A, n_re, n_im, N;
-};
-
-__device__ __forceinline__ float fma_sat(float a, float b, float c)
-{
-    float r;
-    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-// slicer table entry: read-only after initialisation, so the load is a pure function of the address
-__device__ __forceinline__ f32x2 lds_tab(uint32_t addr)
-{
-    f32x2 r;
-    asm("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr));
-    return r;
-}
-
-// Slicer constants of one axis.  The table entry f holds the NEGATED bracket (-lev[f], -lev[min(f+1, n-1)]),
-// f = 0 .. n-1, so that the two candidate differences are one FADD2.  f = floor((t - lev0)/step) clamped to
-// [0, n-1] is computed as u = sat(t*s1 + b1) (u = (x - 1/2)/(n-1) clamped to [0, 1]) followed by
-// w = u*(n-1) + 1.5*2^23, whose low mantissa bits are round(x - 1/2).  A coordinate that lands on the
-// wrong side of an integer by rounding still selects a bracket with the nearest level as an end point,
-// and the differences use the stored level values, so the minimum is bit-identical to the reference's
-// search over all M symbols (IEEE rounding is monotone).
-struct FastAxis {
-    float s1, b1, nm1;
-    uint32_t kaddr;   // table byte address - (0x4b400000 << 3)
-};
-__device__ __forceinline__ FastAxis make_fast_axis(const float *lev, int n, uint32_t tab_addr)
-{
-    FastAxis g;
-    const float span = n > 1 ? lev[n - 1] - lev[0] : 1.f;
-    const float step = n > 1 ? span / (float)(n - 1) : 1.f;
-    g.nm1 = (float)(n > 1 ? n - 1 : 0);
-    g.s1 = n > 1 ? 1.f / span : 0.f;
-    g.b1 = n > 1 ? (-lev[0] / step - 0.5f) / (float)(n - 1) : 0.f;
-    g.kaddr = tab_addr - (0x4b400000u << 3);
-    return g;
-}
-// min over the levels of |t - lev| (bit-exact), one axis
-__device__ __forceinline__ float axis_min_fast(float t, const FastAxis &g)
-{
-    const float u = fma_sat(t, g.s1, g.b1);
-    const float w = fmaf(u, g.nm1, 12582912.f);
-    const f32x2 nl = lds_tab((__float_as_uint(w) << 3) + g.kaddr);
-    const float2 df = add2_bcast(t, nl);
-    return fminf(fabsf(df.x), fabsf(df.y));
-}
-
-__device__ __forceinline__ float unwrap_corr_f(float p, float pprev)
-{
-    // one step of np.unwrap (default period / discont) in float32, op by op
-    const float PI = 3.14159274101257324219f, TWO_PI = 6.28318548202514648438f;
-    const float dd = __fsub_rn(p, pprev);
-    float m = fmodf(__fadd_rn(dd, PI), TWO_PI);
-    if (m != 0.f && m < 0.f) m = __fadd_rn(m, TWO_PI);
-    float ddmod = __fsub_rn(m, PI);
-    if (ddmod == -PI && dd > 0.f) ddmod = PI;
-    float corr = __fsub_rn(ddmod, dd);
-    if (fabsf(dd) < PI) corr = 0.f;
-    return corr;
-}
-__device__ __forceinline__ float2 rotate_f(float2 e, float ph)
-{
-    float s, c;
-    sincosf(ph, &s, &c);
-    return make_float2(e.x * c - e.y * s, e.x * s + e.y * c);
-}
+int bps_par_launch(const BpsFastParams &p, int64_t nstream, cudaStream_t st);            // bps_par.cu
+size_t bps_par_scratch_bytes(int64_t nstream, int64_t L, int64_t A, bool own_idx);
 
 constexpr int FAST_TR = 32;   // rows per tile (= lanes of the tail)
 #ifndef QB_BPS_NR
@@ -224,16 +149,7 @@ __global__ void __launch_bounds__(32 * NW * (1 + NPG)) bps_fast_kernel(BpsFastPa
     uint2 mine = make_uint2(0xffffffffu, 0u);       // (min bits, ballot) of tile row `lane`
 
     // distance of one row to the nearest alphabet point after rotation by this lane's test angle
-    auto dist = [&](float2 ev) {
-        const float2 pa = mul2_bcast(ev.x, c1), pb = mul2_bcast(ev.y, c2);
-        const float tr = __fadd_rn(pa.x, pb.x);     // E[i]*comp[a], unfused (pythran_dsp.py:79)
-        const float ti = __fadd_rn(pa.y, pb.y);
-        float2 dm;
-        dm.x = axis_min_fast(tr, gre);
-        dm.y = axis_min_fast(ti, gim);
-        const float2 sq = sqr2(dm);
-        return fminf(__fadd_rn(sq.x, sq.y), 100.f);                     // :73, :81-82 (NaN -> 100)
-    };
+    auto dist = [&](float2 ev) { return fast_dist(ev, c1, c2, gre, gim); };
 
     if (NPG > 0 && warp >= NW) {
         // =========================== producers: distances of tile m into buffer m & 1 ===========================
@@ -468,7 +384,18 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
     // Few streams: a call lasts as long as one stream is deep -> producer / chain split (bit-identical results, so the
     // choice may follow the launch size).  Option BPS_SPLIT = 0 / 1 (qb_set_option) forces a mapping (tests run both).
     bool split = nstream <= 148 && A <= 64;      // at most one CTA per SM; 2 chain + 8 producer warps at A = 64
-    if (const char e = option_char(OPT_BPS_SPLIT)) split = e == '1' && A <= 64;
+    // Few LONG streams (one capture): the phase-parallel form (bps_par.cu) -- only the running sum and the unwrap stay
+    // serial.  It moves 1 kB of HBM per row through a scratch matrix, so it needs room and few streams.
+    bool par = L >= 32768 && nstream * NW <= 64;
+    if (const char e = option_char(OPT_BPS_SPLIT)) {
+        split = e == '1' && A <= 64;
+        par = e == '2' && L >= 1;
+    }
+    if (par) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bps_par_scratch_bytes(nstream, L, A, idx == nullptr) > free_b / 3)
+            par = false;
+    }
     BpsFastParams p;
     p.E = (const float2 *)E;
     p.comp = (const float2 *)comp;
@@ -484,6 +411,7 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
     p.n_re = (int)n_re;
     p.n_im = (int)n_im;
     p.N = (int)N;
+    if (par) return bps_par_launch(p, nstream, st);
     switch (NW) {
     case 1: return launch_fast<1>(p, nstream, split, st);
     case 2: return launch_fast<2>(p, nstream, split, st);

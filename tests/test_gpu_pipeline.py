@@ -155,13 +155,13 @@ def test_apply_batched_generic_and_fast(env):
     assert rms(out.cpu().numpy() - env.co.apply_segments(E[None], 2, w)) < 1e-13
 
 
-@pytest.fixture(params=["fast", "fast-split", "ws", "simple"])
+@pytest.fixture(params=["fast", "fast-split", "fast-par", "ws", "simple"])
 def bps_kernel(request, qb_option):
     """All BPS kernels: column-per-lane (default where it applies: c64, rectangular alphabet, A a multiple
-    of 32) in its fused mapping and in the producer / chain split it takes for few streams, warp-specialised tiles,
-    phase-by-phase tiles."""
+    of 32) in its fused mapping, in the producer / chain split it takes for few streams and in the phase-parallel form
+    it takes for few long streams (bps_par.cu), warp-specialised tiles, phase-by-phase tiles."""
     if request.param.startswith("fast"):
-        qb_option("BPS_SPLIT", "1" if request.param == "fast-split" else "0")
+        qb_option("BPS_SPLIT", {"fast": "0", "fast-split": "1", "fast-par": "2"}[request.param])
     else:
         qb_option("BPS_KERNEL", request.param)
     return request.param
@@ -617,3 +617,35 @@ def test_receiver_step_is_graph_capturable_with_stage_events(env):
             assert t.equal(a["err"][1], b["err"][1])
         assert t.equal(taps_static, rx.carry_taps(ref))
         assert all(s.elapsed_time(e) > 0 for _, (s, e) in events)
+
+
+@pytest.mark.parametrize("M,A,N,L", [(64, 64, 45, 70001), (16, 32, 21, 40000), (64, 96, 8, 33333), (16, 128, 33, 50000)])
+def test_bps_phase_parallel_form_on_long_streams_with_cycle_slips(env, qb_option, M, A, N, L):
+    """Few long streams take the phase-parallel form (bps_par.cu: distances, running sums, arg-min, unwrap and rotation
+    as separate kernels over a scratch matrix).  A fast Wiener phase walk makes np.unwrap act many times (the serial
+    fold of phase D), a NaN and a huge sample exercise the clamp; phases, indices and rotated symbols must be
+    bit-identical to the fused mapping, with and without the caller's index array, and equal to the oracle's."""
+    t = env.torch
+    alphabet = env.theory.normalised_symbols(M).astype(np.complex64)
+    tables = env.device.BpsTables(A, alphabet, np.complex64, env.dev)
+    rng = np.random.default_rng(L)
+    walk = np.cumsum(rng.standard_normal((3, L)) * 0.08, axis=1)
+    x = alphabet[rng.integers(0, M, (3, L))] * np.exp(1j * walk) + 0.05 * (rng.standard_normal((3, L)) + 1j * rng.standard_normal((3, L)))
+    x = x.astype(np.complex64)
+    x[1, 1234] = np.nan
+    x[2, 4321] = 1e20
+    xd = t.from_numpy(x).to(env.dev)
+    qb_option("BPS_SPLIT", "0")
+    out0, ph0, idx0 = env.device.bps(xd, tables, N)
+    qb_option("BPS_SPLIT", None)                       # default dispatch: phase-parallel for this shape
+    out1, ph1, idx1 = env.device.bps(xd, tables, N)
+    out2, ph2, _ = env.device.bps(xd, tables, N, want_idx=False)
+    assert t.equal(idx0, idx1)
+    assert t.equal(ph0.view(t.int32), ph1.view(t.int32)) and t.equal(ph1.view(t.int32), ph2.view(t.int32))
+    assert t.equal(out0.view(t.float32).view(t.int32), out1.view(t.float32).view(t.int32))
+    assert t.equal(out1.view(t.float32).view(t.int32), out2.view(t.float32).view(t.int32))
+    steps = np.abs(np.diff(ph1[0].cpu().numpy()))
+    assert float(ph1[0].abs().max()) > np.pi / 4, "the walk must leave the search range: unwrap has acted"
+    ang = np.linspace(-np.pi / 4, np.pi / 4, A, endpoint=False, dtype=np.float32).reshape(1, -1)
+    idr = env.co.bps_streams(x, ang, alphabet, N)
+    assert np.array_equal(idx1.cpu().numpy()[:, N:L - N], idr[:, N:L - N])
