@@ -50,7 +50,7 @@ __device__ __forceinline__ void fbar_arrive(int count)
 }
 
 int bps_par_launch(const BpsFastParams &p, int64_t nstream, cudaStream_t st);            // bps_par.cu
-size_t bps_par_scratch_bytes(int64_t nstream, int64_t L, int64_t A, bool own_idx);
+bool bps_par_wanted(int64_t nstream, int64_t L, int64_t A, bool own_idx, int elem);
 
 constexpr int FAST_TR = 32;   // rows per tile (= lanes of the tail)
 #ifndef QB_BPS_NR
@@ -384,18 +384,9 @@ int bps_fast_dispatch(const void *E, int64_t nstream, int64_t stream_stride, int
     // Few streams: a call lasts as long as one stream is deep -> producer / chain split (bit-identical results, so the
     // choice may follow the launch size).  Option BPS_SPLIT = 0 / 1 (qb_set_option) forces a mapping (tests run both).
     bool split = nstream <= 148 && A <= 64;      // at most one CTA per SM; 2 chain + 8 producer warps at A = 64
-    // Few LONG streams (one capture): the phase-parallel form (bps_par.cu) -- only the running sum and the unwrap stay
-    // serial.  It moves 1 kB of HBM per row through a scratch matrix, so it needs room and few streams.
-    bool par = L >= 32768 && nstream * NW <= 64;
-    if (const char e = option_char(OPT_BPS_SPLIT)) {
-        split = e == '1' && A <= 64;
-        par = e == '2' && L >= 1;
-    }
-    if (par) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bps_par_scratch_bytes(nstream, L, A, idx == nullptr) > free_b / 3)
-            par = false;
-    }
+    if (const char e = option_char(OPT_BPS_SPLIT)) split = e == '1' && A <= 64;
+    // few LONG streams (one capture): the phase-parallel form (bps_par.cu)
+    const bool par = bps_par_wanted(nstream, L, A, idx == nullptr, 4);
     BpsFastParams p;
     p.E = (const float2 *)E;
     p.comp = (const float2 *)comp;

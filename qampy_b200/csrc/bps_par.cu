@@ -13,7 +13,8 @@
 //                                                                                     per step
 //   E  rotation of the input by the phase, edges (phaserecovery.py:155-159)        -- independent
 //
-// The matrix lives in HBM in TILES of 128 rows: D[stream][tile][angle][128 rows + 4 of padding] (one float per entry).
+// The matrix lives in HBM in TILES of 128 rows: D[stream][tile][angle][128 rows + 16 bytes of padding] (one float, or one
+// double for complex128 signals, per entry).
 // Phase A's lane owns an angle and stores 8 consecutive rows as two 16-byte vectors.  Phase B's lane owns an angle and
 // walks down its column: a tile of 128 rows x 32 angles is one contiguous 16.5 kB block that comes and goes as ONE bulk
 // copy each way (cp.async.bulk + mbarrier, seven tiles on their way in, up to four out); LDS.128 -> four dependent
@@ -26,29 +27,61 @@
 // for a batch that has one (2.7 cycles per row).  1 kB of HBM traffic per row, which is why this form is for few
 // streams only: many streams keep the fused kernel, whose distances never leave the lane.
 //
+// complex128 signals and alphabets without a rectangular grid take the same phases with the distance of bps.cu (generic
+// slicer / search over the alphabet) in phase A and double-precision sums (DADD chain: 8.8 cycles per row).
+//
 // One capture of two polarisations, 64 angles (scratch/bps_par_time.py): 1e7 rows 63 ms against 408 ms in the producer /
 // chain mapping (12.4 against 80 cycles per row), 1e6 rows 6.5 against 40 ms, 2^17 rows 1.2 against 5.3 ms; indices and
 // phases identical.
 #include <stdlib.h>
 
 #include "bps_dist.cuh"
+#include "bps_generic.cuh"
 
 namespace qb {
 
-constexpr int PAR_NR = 8;             // rows per group of phase A (two 16-byte stores per lane)
+constexpr int PAR_NR = 8;             // rows per group of phase A (whole 16-byte stores per lane)
 constexpr int PAR_RC = 1024;          // rows per CTA of phase A
-constexpr int PAR_TR = 128;           // rows per staged tile of phase B
-constexpr int PAR_TRP = PAR_TR + 4;   // pitch of an angle column inside a tile, in HBM and in shared memory alike: the
-                                      // LDS.128 of the 32 lanes fall into disjoint banks, and a tile is ONE bulk copy
-constexpr int PAR_ST = 12;            // stages of its ring
-constexpr int PAR_LD = 7;             // tiles on their way in; the other PAR_ST - PAR_LD - 1 stages may still be on their way out
+constexpr int PAR_TR = 128;           // rows per tile of the matrix
 constexpr int PAR_UB = 512;           // rows per batch of phase D
 constexpr int PAR_UST = 8;            // batches in the ring of phase D (6 in flight)
 
-// floats of one stream's matrix: Lp / 128 tiles of A columns of 132
-__host__ __device__ __forceinline__ long long par_stream_floats(int A, long long Lp) { return Lp / PAR_TR * A * PAR_TRP; }
+// T = float (complex64 signals) or double (complex128: the reference's default dtype)
+template <typename T>
+struct ParGeom {
+    static constexpr int EV = 16 / sizeof(T);              // entries per 16-byte vector
+    // pitch of an angle column inside a tile, in HBM and in shared memory alike: one vector of padding, so that the
+    // 128-bit shared-memory accesses of the 32 lanes fall into disjoint banks and a tile is ONE bulk copy
+    static constexpr int TRP = PAR_TR + EV;
+    static constexpr int ST = sizeof(T) == 4 ? 12 : 6;     // stages of phase B's ring (203 kB / 200 kB)
+    static constexpr int LD = sizeof(T) == 4 ? 7 : 3;      // tiles on their way in; ST - LD - 1 may be on their way out
+};
+// entries of one stream's matrix: Lp / 128 tiles of A columns
+template <typename T>
+__host__ __device__ __forceinline__ long long par_stream_elems(int A, long long Lp)
+{
+    return Lp / PAR_TR * A * ParGeom<T>::TRP;
+}
+// entry (angle a, row i) of a stream's matrix: ((tile i / 128) * A + a) * TRP + i % 128
+template <typename T>
+__device__ __forceinline__ long long par_at(int A, int a, long long i)
+{
+    return ((i / PAR_TR) * A + a) * ParGeom<T>::TRP + i % PAR_TR;
+}
 
-// ---- A: distances ---------------------------------------------------------------------------------------------------
+// what phases B .. E need to know about a call
+template <typename T>
+struct ParCall {
+    const cx<T> *E;
+    const T *angles;
+    int32_t *idx;      // the caller's index array or nullptr
+    T *ph;
+    cx<T> *Eout;
+    long long stream_stride, L;
+    int A, N;
+};
+
+// ---- A (complex64, rectangular alphabet): distances with the packed slicer of bps_fast.cu -----------------------------
 template <int NW>
 __global__ void __launch_bounds__(64 * NW) bps_par_dist_kernel(BpsFastParams p, float *D, long long Lp)
 {
@@ -81,8 +114,8 @@ __global__ void __launch_bounds__(64 * NW) bps_par_dist_kernel(BpsFastParams p, 
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c1), "=l"(c2) : "r"(smem_u32(bounce + tid)) : "memory");
 
     const float2 *E = p.E + (long long)blockIdx.y * p.stream_stride;
-    // entry (angle a, row i) of this stream: ((tile i / 128) * A + a) * 132 + i % 128
-    float *col = D + (long long)blockIdx.y * par_stream_floats(p.A, Lp) + (long long)(colw * 32 + lane) * PAR_TRP;
+    float *mat = D + (long long)blockIdx.y * par_stream_elems<float>(p.A, Lp);
+    const int a = colw * 32 + lane;
     const long long r0 = (long long)blockIdx.x * PAR_RC + (long long)part * (PAR_RC / 2);
     const long long last = p.L - 1;
 #pragma unroll 1
@@ -95,15 +128,65 @@ __global__ void __launch_bounds__(64 * NW) bps_par_dist_kernel(BpsFastParams p, 
         float c[PAR_NR];
 #pragma unroll
         for (int u = 0; u < PAR_NR; u++) c[u] = fast_dist(e[u], c1, c2, gre, gim);
-        float4 *dst = reinterpret_cast<float4 *>(col + (i / PAR_TR) * ((long long)p.A * PAR_TRP) + (i % PAR_TR));
+        float4 *dst = reinterpret_cast<float4 *>(mat + par_at<float>(p.A, a, i));
         dst[0] = make_float4(c[0], c[1], c[2], c[3]);
         dst[1] = make_float4(c[4], c[5], c[6], c[7]);
     }
 }
 
+// ---- A (any dtype, any alphabet): distances with the generic slicer / the search over the alphabet of bps.cu -----------
+template <typename T>
+__global__ void __launch_bounds__(256) bps_par_dist_generic_kernel(BpsParams<T> p, T *D, long long Lp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = p.A;
+    cx<T> *comp = reinterpret_cast<cx<T> *>(smem_raw);  // [A]
+    cx<T> *syms = comp + A;                             // [M] (search) or level pairs (slicer)
+    const bool slicer = p.n_re > 0;
+    const int npr = slicer ? max(p.n_re - 1, 1) : 0, npi = slicer ? max(p.n_im - 1, 1) : 0;
+    cx<T> *pre = syms, *pim = syms + npr;
+    for (int c = tid; c < A; c += 256) comp[c] = p.comp[c];
+    AxisGrid<T> gre, gim;
+    gre.scale = gre.bias = gim.scale = gim.bias = (T)0;
+    gre.npair = gim.npair = 1;
+    if (slicer) {
+        for (int c = tid; c < npr; c += 256) pre[c] = make_cx<T>(p.lev_re[c], p.lev_re[min(c + 1, p.n_re - 1)]);
+        for (int c = tid; c < npi; c += 256) pim[c] = make_cx<T>(p.lev_im[c], p.lev_im[min(c + 1, p.n_im - 1)]);
+        gre = make_grid(p.lev_re, p.n_re);
+        gim = make_grid(p.lev_im, p.n_im);
+    } else {
+        for (int c = tid; c < p.M; c += 256) syms[c] = p.symbols[c];
+    }
+    __syncthreads();
+    const cx<T> *E = p.E + (long long)blockIdx.y * p.stream_stride;
+    T *mat = D + (long long)blockIdx.y * par_stream_elems<T>(A, Lp);
+    const int nw = A / 32;
+    const long long last = p.L - 1;
+    // units of work: (group of 8 rows, block of 32 angles); lane = angle
+    for (int u = warp; u < nw * (PAR_RC / PAR_NR); u += 8) {
+        const int cb = u % nw, g = u / nw;
+        const long long i = (long long)blockIdx.x * PAR_RC + (long long)g * PAR_NR;
+        if (i >= p.L) break;
+        const int a = cb * 32 + lane;
+        const cx<T> c = comp[a];
+        T d[PAR_NR];
+#pragma unroll
+        for (int k = 0; k < PAR_NR; k++) d[k] = min_distance<T>(E[min(i + k, last)], c, slicer, pre, pim, gre, gim, syms, p.M);
+        T *dst = mat + par_at<T>(A, a, i);
+        if constexpr (sizeof(T) == 4) {
+            reinterpret_cast<float4 *>(dst)[0] = make_float4(d[0], d[1], d[2], d[3]);
+            reinterpret_cast<float4 *>(dst)[1] = make_float4(d[4], d[5], d[6], d[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < PAR_NR / 2; k++) reinterpret_cast<double2 *>(dst)[k] = make_double2(d[2 * k], d[2 * k + 1]);
+        }
+    }
+}
+
 // ---- B: running sums down the columns, in place ---------------------------------------------------------------------
-// one warp per (stream, block of 32 angles); lane = angle.  Tiles come and go as bulk copies (one 512-byte column piece
-// per lane and tile each way): the warp's own instructions per row are 1/4 LDS.128 + FADD + 1/4 STS.128.
+// one warp per (stream, block of 32 angles); lane = angle.  A tile comes and goes as ONE bulk copy each way: the warp's
+// own instructions per row are the add and a share of one 128-bit shared-memory load and store.
 __device__ __forceinline__ void bulk_s2g(void *gmem, const void *smem, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes)
@@ -117,77 +200,91 @@ __device__ __forceinline__ void bulk_wait_read()
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-__global__ void __launch_bounds__(32) bps_par_csum_kernel(float *D, long long Lp, long long L, int A)
+template <typename T>
+__global__ void __launch_bounds__(32) bps_par_csum_kernel(T *D, long long Lp, long long L, int A)
 {
+    using G = ParGeom<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);                    // [PAR_ST][32][PAR_TRP]
-    __shared__ uint64_t full[PAR_ST];
+    T *tiles = reinterpret_cast<T *>(smem_raw);                            // [ST][32][TRP]
+    __shared__ uint64_t full[G::ST];
     const int lane = threadIdx.x;
     const int nw = A / 32;
     const int s = blockIdx.x / nw, cb = blockIdx.x % nw;
-    float *base = D + (long long)s * par_stream_floats(A, Lp) + (long long)cb * 32 * PAR_TRP;   // tile t: + t * A * 132
-    const long long tstride = (long long)A * PAR_TRP;
+    T *base = D + (long long)s * par_stream_elems<T>(A, Lp) + (long long)cb * 32 * G::TRP;   // tile t: + t * A * TRP
+    const long long tstride = (long long)A * G::TRP;
     const long long ntiles = (L + PAR_TR - 1) / PAR_TR;
-    constexpr uint32_t TILE_BYTES = 32 * PAR_TRP * sizeof(float);          // 32 columns of this block: contiguous
+    constexpr uint32_t TILE_BYTES = 32 * G::TRP * sizeof(T);               // the 32 columns of this block: contiguous
     if (lane == 0) {
-        for (int k = 0; k < PAR_ST; k++) mbar_init(&full[k], 1);
+        for (int k = 0; k < G::ST; k++) mbar_init(&full[k], 1);
         mbar_fence_init();
     }
     __syncwarp();
 
     auto load = [&](long long t) {          // lane 0
         if (t < ntiles) {
-            const int st = (int)(t % PAR_ST);
+            const int st = (int)(t % G::ST);
             mbar_arrive_expect_tx(&full[st], TILE_BYTES);
-            tma_bulk_g2s(tiles + (size_t)st * 32 * PAR_TRP, base + t * tstride, TILE_BYTES, &full[st]);
+            tma_bulk_g2s(tiles + (size_t)st * 32 * G::TRP, base + t * tstride, TILE_BYTES, &full[st]);
         }
     };
     if (lane == 0)
-        for (int t = 0; t < PAR_LD; t++) load(t);
-    float csum = 0.f;
+        for (int t = 0; t < G::LD; t++) load(t);
+    T csum = 0;
     for (long long t = 0; t < ntiles; t++) {
         if (lane == 0) {
-            // tile t + PAR_LD lands in the stage of tile t + PAR_LD - PAR_ST, whose store must have read it: the stores of
-            // the PAR_ST - PAR_LD - 1 tiles after that one may still be pending
-            bulk_wait_read<PAR_ST - PAR_LD - 1>();
-            load(t + PAR_LD);
+            // tile t + LD lands in the stage of tile t + LD - ST, whose store must have read it: the stores of the
+            // ST - LD - 1 tiles after that one may still be pending
+            bulk_wait_read<G::ST - G::LD - 1>();
+            load(t + G::LD);
         }
-        mbar_wait(&full[t % PAR_ST], (uint32_t)((t / PAR_ST) & 1));
-        float *stage = tiles + (size_t)(t % PAR_ST) * 32 * PAR_TRP;
-        const uint32_t my = smem_u32(stage + lane * PAR_TRP);
-        // Software pipeline in groups of 4 rows: the LDS.128 of group g + 2 and the STS.128 of group g - 1 sit between
-        // the four dependent FADDs of group g (volatile, so that they stay where they are written): a lone warp
-        // issues one instruction per ~2.5 cycles, the FADD chain needs one per 4.4 -- the memory instructions ride in
-        // the chain's shadow instead of queueing before and after it.
-        auto lds = [&](int g) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(my + 16u * g));
-            return v;
-        };
-        auto sts = [&](int g, const float4 &v) {
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16u * g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        };
-        constexpr int NG = PAR_TR / 4;
-        float4 v0 = lds(0), v1 = lds(1), done = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t == 0) v0.x = 0.f;                                            // row 0 is never added (pythran_dsp.py:30)
+        mbar_wait(&full[t % G::ST], (uint32_t)((t / G::ST) & 1));
+        T *stage = tiles + (size_t)(t % G::ST) * 32 * G::TRP;
+        if constexpr (sizeof(T) == 4) {
+            const uint32_t my = smem_u32(stage + lane * G::TRP);
+            // Software pipeline in groups of 4 rows: the LDS.128 of group g + 2 and the STS.128 of group g - 1 sit
+            // between the four dependent FADDs of group g (volatile, so that they stay where they are written)
+            auto lds = [&](int g) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(my + 16u * g));
+                return v;
+            };
+            auto sts = [&](int g, const float4 &v) {
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16u * g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            };
+            constexpr int NG = PAR_TR / 4;
+            float4 v0 = lds(0), v1 = lds(1), done = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t == 0) v0.x = 0.f;                                        // row 0 is never added (pythran_dsp.py:30)
 #pragma unroll
-        for (int g = 0; g < NG; g++) {
-            float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
-            csum = __fadd_rn(csum, v0.x);                                  // :33/:36, sequential
-            v0.x = csum;
-            if (g + 2 < NG) v2 = lds(g + 2);
-            csum = __fadd_rn(csum, v0.y);
-            v0.y = csum;
-            if (g > 0) sts(g - 1, done);
-            csum = __fadd_rn(csum, v0.z);
-            v0.z = csum;
-            csum = __fadd_rn(csum, v0.w);
-            v0.w = csum;
-            done = v0;
-            v0 = v1;
-            v1 = v2;
+            for (int g = 0; g < NG; g++) {
+                float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                csum = __fadd_rn(csum, v0.x);                              // :33/:36, sequential
+                v0.x = csum;
+                if (g + 2 < NG) v2 = lds(g + 2);
+                csum = __fadd_rn(csum, v0.y);
+                v0.y = csum;
+                if (g > 0) sts(g - 1, done);
+                csum = __fadd_rn(csum, v0.z);
+                v0.z = csum;
+                csum = __fadd_rn(csum, v0.w);
+                v0.w = csum;
+                done = v0;
+                v0 = v1;
+                v1 = v2;
+            }
+            sts(NG - 1, done);
+        } else {
+            double2 *my = reinterpret_cast<double2 *>(stage + lane * G::TRP);
+#pragma unroll 8
+            for (int g = 0; g < PAR_TR / 2; g++) {
+                double2 v = my[g];
+                if (t == 0 && g == 0) v.x = 0.;                            // row 0 is never added (pythran_dsp.py:30)
+                csum = __dadd_rn(csum, v.x);                               // :33/:36, sequential
+                v.x = csum;
+                csum = __dadd_rn(csum, v.y);
+                v.y = csum;
+                my[g] = v;
+            }
         }
-        sts(NG - 1, done);
         fence_proxy_async();                                               // the sums above, seen by the copy engine
         __syncwarp();
         if (lane == 0) {
@@ -200,44 +297,43 @@ __global__ void __launch_bounds__(32) bps_par_csum_kernel(float *D, long long Lp
 }
 
 // ---- C: window differences and their first arg-min; thread = output row ----------------------------------------------
-__global__ void __launch_bounds__(256) bps_par_argmin_kernel(const float *C, long long Lp, long long L, int A, int N,
+template <typename T>
+__global__ void __launch_bounds__(256) bps_par_argmin_kernel(const T *C, long long Lp, long long L, int A, int N,
                                                              int32_t *idx)
 {
     const long long lo = N < L ? N : L;
     const long long hi = (L - N > lo) ? L - N : lo;
     const long long j = lo + (long long)blockIdx.x * 256 + threadIdx.x;
     if (j >= hi) return;
-    const float *cs = C + (long long)blockIdx.y * par_stream_floats(A, Lp);
-    const long long iu = j + N, id = j - N;                  // csum[i], csum[i - 2N] with i = j + N
-    const float *up = cs + (iu / PAR_TR) * ((long long)A * PAR_TRP) + iu % PAR_TR;
-    const float *dn = cs + (id / PAR_TR) * ((long long)A * PAR_TRP) + id % PAR_TR;
-    unsigned best = 0xffffffffu;
+    const T *cs = C + (long long)blockIdx.y * par_stream_elems<T>(A, Lp);
+    const T *up = cs + par_at<T>(A, 0, j + N), *dn = cs + par_at<T>(A, 0, j - N);   // csum[i], csum[i - 2N], i = j + N
+    T best = (T)1000.;                                       // dmin0 = 1000 (:31): nothing below it -> idx stays 0
     int bk = 0;
 #pragma unroll 8
     for (int a = 0; a < A; a++) {
-        const unsigned db = __float_as_uint(__fsub_rn(__ldg(up + a * PAR_TRP), __ldg(dn + a * PAR_TRP)));
-        if (db < best) {                                     // >= +0: orders like an unsigned; strict <: first minimum (:39)
-            best = db;
+        const T v = sub_rn(__ldg(up + a * ParGeom<T>::TRP), __ldg(dn + a * ParGeom<T>::TRP));
+        if (v < best) {                                      // strict <, ascending angles: first minimum (:39)
+            best = v;
             bk = a;
         }
     }
-    if (best >= 0x447a0000u) bk = 0;                         // dmin0 = 1000 (:31): nothing below it -> idx stays 0
     idx[(long long)blockIdx.y * L + j] = bk;
 }
 
 // ---- D: phases and their unwrap; one warp per stream, lane = row -------------------------------------------------------
-__global__ void __launch_bounds__(32) bps_par_unwrap_kernel(const int32_t *idx, const float *angles, int A, long long L,
-                                                            int N, float *ph)
+template <typename T>
+__global__ void __launch_bounds__(32) bps_par_unwrap_kernel(const int32_t *idx, const T *angles, int A, long long L,
+                                                            int N, T *ph)
 {
-    __shared__ float angs[128];
+    __shared__ T angs[128];
     __shared__ int32_t ring[PAR_UST][PAR_UB];
     const int lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
     const long long lo = N < L ? N : L;
     const long long hi = (L - N > lo) ? L - N : lo;
     const int32_t *ix = idx + (long long)blockIdx.x * L;
-    float *pho = ph + (long long)blockIdx.x * L;
-    for (int c = lane; c < A; c += 32) angs[c] = angles ? angles[c] : 0.f;
+    T *pho = ph + (long long)blockIdx.x * L;
+    for (int c = lane; c < A; c += 32) angs[c] = angles ? angles[c] : (T)0;
     const long long nb = (hi - lo + PAR_UB - 1) / PAR_UB;
     auto load = [&](long long b) {
         if (b < nb) {
@@ -251,14 +347,14 @@ __global__ void __launch_bounds__(32) bps_par_unwrap_kernel(const int32_t *idx, 
     };
     for (int b = 0; b < PAR_UST - 2; b++) load(b);
     __syncwarp();
-    float cum = 0.f, p4prev = 0.f;
+    T cum = 0, p4prev = 0;
     constexpr int KB = PAR_UB / 32;
     for (long long b = 0; b < nb; b++) {
         load(b + PAR_UST - 2);
         cp_async_wait<PAR_UST - 2>();
         __syncwarp();
-        // everything that does not depend on the running correction, for the 8 steps of the batch at once
-        float p4[KB], pp[KB];
+        // everything that does not depend on the running correction, for the 16 steps of the batch at once
+        T p4[KB], pp[KB];
         bool valid[KB], cand[KB];
         unsigned anyc = 0u;
 #pragma unroll
@@ -266,46 +362,46 @@ __global__ void __launch_bounds__(32) bps_par_unwrap_kernel(const int32_t *idx, 
             const long long j = lo + b * PAR_UB + 32 * k + lane;
             valid[k] = j < hi;
             const int bk = valid[k] ? ring[b % PAR_UST][32 * k + lane] : 0;
-            p4[k] = __fmul_rn(angs[bk], 4.f);
+            p4[k] = mul_rn(angs[bk], (T)4);
         }
 #pragma unroll
         for (int k = 0; k < KB; k++) {
             const long long j = lo + b * PAR_UB + 32 * k + lane;
-            pp[k] = __shfl_up_sync(FULL, p4[k], 1);
-            const float carry = k == 0 ? p4prev : __shfl_sync(FULL, p4[k > 0 ? k - 1 : 0], 31);   // a step before the last is full
+            pp[k] = shfl_up(p4[k], 1);
+            const T carry = k == 0 ? p4prev : shfl_idx(p4[k > 0 ? k - 1 : 0], 31);   // a step before the last is full
             if (lane == 0) pp[k] = carry;
             // np.unwrap only acts where |dd| >= pi
-            cand[k] = valid[k] && j > lo && !(fabsf(__fsub_rn(p4[k], pp[k])) < 3.14159274101257324219f);
+            cand[k] = valid[k] && j > lo && !(fabs(sub_rn(p4[k], pp[k])) < Pi<T>::pi());
             anyc |= __ballot_sync(FULL, cand[k]);
         }
         if (anyc == 0u) {                                   // the usual batch: no correction, the running sum stands
 #pragma unroll
             for (int k = 0; k < KB; k++)
-                if (valid[k]) pho[lo + b * PAR_UB + 32 * k + lane] = __fadd_rn(p4[k], cum) / 4.f;
+                if (valid[k]) pho[lo + b * PAR_UB + 32 * k + lane] = add_rn(p4[k], cum) / (T)4;
         } else {
 #pragma unroll
             for (int k = 0; k < KB; k++) {
-                const float corr = cand[k] ? unwrap_corr_f(p4[k], pp[k]) : 0.f;
-                unsigned mask = __ballot_sync(FULL, corr != 0.f);
-                float mycum = cum;
+                const T corr = cand[k] ? unwrap_corr<T>(p4[k], pp[k]) : (T)0;
+                unsigned mask = __ballot_sync(FULL, corr != (T)0);
+                T mycum = cum;
                 while (mask) {   // fold the (rare) non-zero corrections in row order: exact sequential sum
                     const int e = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const float ce = __shfl_sync(FULL, corr, e);
-                    cum = __fadd_rn(cum, ce);
+                    const T ce = shfl_idx(corr, e);
+                    cum = add_rn(cum, ce);
                     if (lane >= e) mycum = cum;
                 }
-                if (valid[k]) pho[lo + b * PAR_UB + 32 * k + lane] = __fadd_rn(p4[k], mycum) / 4.f;
+                if (valid[k]) pho[lo + b * PAR_UB + 32 * k + lane] = add_rn(p4[k], mycum) / (T)4;
             }
         }
         // the last valid row of the batch (only the capture's last batch is not full)
         if (b + 1 < nb) {
-            p4prev = __shfl_sync(FULL, p4[KB - 1], 31);
+            p4prev = shfl_idx(p4[KB - 1], 31);
         } else {
 #pragma unroll
             for (int k = 0; k < KB; k++) {
                 const unsigned vm = __ballot_sync(FULL, valid[k]);
-                if (vm) p4prev = __shfl_sync(FULL, p4[k], 31 - __clz(vm));
+                if (vm) p4prev = shfl_idx(p4[k], 31 - __clz(vm));
             }
         }
         __syncwarp();
@@ -313,7 +409,11 @@ __global__ void __launch_bounds__(32) bps_par_unwrap_kernel(const int32_t *idx, 
 }
 
 // ---- E: edges and rotation --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bps_par_rotate_kernel(BpsFastParams p)
+__device__ __forceinline__ float2 par_rotate(float2 e, float ph) { return rotate_f(e, ph); }          // as bps_fast.cu
+__device__ __forceinline__ double2 par_rotate(double2 e, double ph) { return rotate<double>(e, ph); }  // as bps.cu
+
+template <typename T>
+__global__ void __launch_bounds__(256) bps_par_rotate_kernel(ParCall<T> p)
 {
     const long long L = p.L;
     const int N = p.N;
@@ -321,35 +421,40 @@ __global__ void __launch_bounds__(256) bps_par_rotate_kernel(BpsFastParams p)
     const long long hi = (L - N > lo) ? L - N : lo;
     const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
     if (j >= L) return;
-    const float2 *E = p.E + (long long)blockIdx.y * p.stream_stride;
+    const cx<T> *E = p.E + (long long)blockIdx.y * p.stream_stride;
     const long long o = (long long)blockIdx.y * L + j;
     if (j < lo || j >= hi) {
         // edges: idx = 0 -> ph = angles[0], not unwrapped (phaserecovery.py:155 touches [N:-N] only)
-        const float a0 = p.angles ? p.angles[0] : 0.f;
+        const T a0 = p.angles ? p.angles[0] : (T)0;
         if (p.idx) p.idx[o] = 0;
         if (p.ph) p.ph[o] = a0;
-        if (p.Eout) p.Eout[o] = rotate_f(E[j], a0);
+        if (p.Eout) p.Eout[o] = par_rotate(E[j], a0);
     } else if (p.Eout && p.ph) {
-        p.Eout[o] = rotate_f(E[j], p.ph[o]);
+        p.Eout[o] = par_rotate(E[j], p.ph[o]);
     }
 }
 
 static size_t par_dist_smem(int NW, int n_re, int n_im) { return (size_t)(n_re + n_im) * 8 + 8 + 16 + (size_t)64 * NW * 16; }
 
+static long long par_padded_rows(long long L) { return (L + PAR_RC - 1) / PAR_RC * PAR_RC; }
+
 // bytes of scratch the phase-parallel form needs (the distance / running-sum matrix and, unless the caller wants the
-// indices, an index array)
-size_t bps_par_scratch_bytes(int64_t nstream, int64_t L, int64_t A, bool own_idx)
+// indices, an index array); elem = 4 (complex64 signals) or 8
+size_t bps_par_scratch_bytes(int64_t nstream, int64_t L, int64_t A, bool own_idx, int elem)
 {
-    const long long Lp = (L + PAR_RC - 1) / PAR_RC * PAR_RC;
-    return (size_t)nstream * par_stream_floats((int)A, Lp) * sizeof(float) + (own_idx ? (size_t)nstream * L * sizeof(int32_t) : 0);
+    const long long Lp = par_padded_rows(L);
+    const size_t mat = elem == 4 ? (size_t)par_stream_elems<float>((int)A, Lp) * 4 : (size_t)par_stream_elems<double>((int)A, Lp) * 8;
+    return (size_t)nstream * mat + (own_idx ? (size_t)nstream * L * sizeof(int32_t) : 0);
 }
 
-template <int NW>
-static int launch_par(const BpsFastParams &p, int64_t nstream, cudaStream_t st)
+// phases B .. E behind a phase A that `launch_a(D, Lp)` enqueues
+template <typename T, typename LaunchA>
+static int par_run(const ParCall<T> &c, int64_t nstream, cudaStream_t st, LaunchA launch_a)
 {
-    const long long L = p.L, Lp = (L + PAR_RC - 1) / PAR_RC * PAR_RC;
-    const size_t mat = (size_t)nstream * par_stream_floats(p.A, Lp) * sizeof(float);
-    float *D = nullptr;
+    using G = ParGeom<T>;
+    const long long L = c.L, Lp = par_padded_rows(L);
+    const size_t mat = (size_t)nstream * par_stream_elems<T>(c.A, Lp) * sizeof(T);
+    T *D = nullptr;
     int32_t *own_idx = nullptr;
     {
         // keep the scratch cached in the device's pool between calls (as the host entry points do): re-allocating 5 GB
@@ -362,7 +467,7 @@ static int launch_par(const BpsFastParams &p, int64_t nstream, cudaStream_t st)
         QB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
     QB_CUDA_CHECK(cudaMallocAsync(&D, mat, st));
-    int32_t *idx = p.idx;
+    int32_t *idx = c.idx;
     if (!idx) {
         cudaError_t e = cudaMallocAsync(&own_idx, (size_t)nstream * L * sizeof(int32_t), st);
         if (e != cudaSuccess) {
@@ -373,26 +478,26 @@ static int launch_par(const BpsFastParams &p, int64_t nstream, cudaStream_t st)
     }
     int rc = QB_OK;
     do {
-        const long long lo = p.N < L ? p.N : L, hi = (L - p.N > lo) ? L - p.N : lo;
+        const long long lo = c.N < L ? c.N : L, hi = (L - c.N > lo) ? L - c.N : lo;
         if (hi > lo) {
-            bps_par_dist_kernel<NW><<<dim3((unsigned)(Lp / PAR_RC), (unsigned)nstream), 64 * NW, par_dist_smem(NW, p.n_re, p.n_im), st>>>(p, D, Lp);
+            launch_a(D, Lp);
             count_launch();
-            const size_t smem_b = (size_t)PAR_ST * 32 * PAR_TRP * sizeof(float);   // + the static mbarriers
-            if (cudaFuncSetAttribute(bps_par_csum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess) {
+            const size_t smem_b = (size_t)G::ST * 32 * G::TRP * sizeof(T);   // + the static mbarriers
+            if (cudaFuncSetAttribute(bps_par_csum_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess) {
                 rc = set_error(QB_ERR_CUDA, "bps: cudaFuncSetAttribute failed");
                 break;
             }
-            bps_par_csum_kernel<<<(unsigned)(nstream * NW), 32, smem_b, st>>>(D, Lp, L, p.A);
+            bps_par_csum_kernel<T><<<(unsigned)(nstream * (c.A / 32)), 32, smem_b, st>>>(D, Lp, L, c.A);
             count_launch();
-            bps_par_argmin_kernel<<<dim3((unsigned)((hi - lo + 255) / 256), (unsigned)nstream), 256, 0, st>>>(D, Lp, L, p.A, p.N, idx);
+            bps_par_argmin_kernel<T><<<dim3((unsigned)((hi - lo + 255) / 256), (unsigned)nstream), 256, 0, st>>>(D, Lp, L, c.A, c.N, idx);
             count_launch();
-            if (p.ph) {
-                bps_par_unwrap_kernel<<<(unsigned)nstream, 32, 0, st>>>(idx, p.angles, p.A, L, p.N, p.ph);
+            if (c.ph) {
+                bps_par_unwrap_kernel<T><<<(unsigned)nstream, 32, 0, st>>>(idx, c.angles, c.A, L, c.N, c.ph);
                 count_launch();
             }
         }
         if (L > 0) {
-            bps_par_rotate_kernel<<<dim3((unsigned)((L + 255) / 256), (unsigned)nstream), 256, 0, st>>>(p);
+            bps_par_rotate_kernel<T><<<dim3((unsigned)((L + 255) / 256), (unsigned)nstream), 256, 0, st>>>(c);
             count_launch();
         }
         if (cudaGetLastError() != cudaSuccess) rc = set_error(QB_ERR_CUDA, "bps: launch of the phase-parallel kernels failed");
@@ -402,15 +507,55 @@ static int launch_par(const BpsFastParams &p, int64_t nstream, cudaStream_t st)
     return rc;
 }
 
-// phase-parallel form; same contract as launch_fast in bps_fast.cu
+// Is the phase-parallel form the one to take?  Few LONG streams (one capture): only the running sum and the unwrap stay
+// serial.  It moves 1 kB (complex64) of HBM per row through a scratch matrix, so it needs room and few streams.  Option
+// BPS_SPLIT = 2 (qb_set_option) forces it, 0 / 1 exclude it (tests run all mappings).
+bool bps_par_wanted(int64_t nstream, int64_t L, int64_t A, bool own_idx, int elem)
+{
+    if (A % 32 != 0 || A > 128 || nstream < 1) return false;
+    bool par = L >= 32768 && nstream * (A / 32) <= 64;
+    if (const char e = option_char(OPT_BPS_SPLIT)) par = e == '2' && L >= 1;
+    if (par) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bps_par_scratch_bytes(nstream, L, A, own_idx, elem) > free_b / 3)
+            par = false;
+    }
+    return par;
+}
+
+template <int NW>
+static int launch_par_fast(const BpsFastParams &p, int64_t nstream, cudaStream_t st)
+{
+    ParCall<float> c{p.E, p.angles, p.idx, p.ph, p.Eout, p.stream_stride, p.L, p.A, p.N};
+    return par_run<float>(c, nstream, st, [&](float *D, long long Lp) {
+        bps_par_dist_kernel<NW><<<dim3((unsigned)(Lp / PAR_RC), (unsigned)nstream), 64 * NW, par_dist_smem(NW, p.n_re, p.n_im), st>>>(p, D, Lp);
+    });
+}
+
+// complex64 signal on a rectangular alphabet (called from bps_fast.cu); same contract as launch_fast there
 int bps_par_launch(const BpsFastParams &p, int64_t nstream, cudaStream_t st)
 {
     switch (p.A / 32) {
-    case 1: return launch_par<1>(p, nstream, st);
-    case 2: return launch_par<2>(p, nstream, st);
-    case 3: return launch_par<3>(p, nstream, st);
-    default: return launch_par<4>(p, nstream, st);
+    case 1: return launch_par_fast<1>(p, nstream, st);
+    case 2: return launch_par_fast<2>(p, nstream, st);
+    case 3: return launch_par_fast<3>(p, nstream, st);
+    default: return launch_par_fast<4>(p, nstream, st);
     }
 }
+
+// any dtype, any alphabet (called from bps.cu); returns 1 if the shape is not covered (caller keeps its tile kernels)
+template <typename T>
+int bps_par_generic_launch(const BpsParams<T> &p, int64_t nstream, cudaStream_t st)
+{
+    const bool slicer = p.n_re > 0;
+    const size_t smem_a = (size_t)(p.A + (slicer ? p.n_re + p.n_im : p.M)) * sizeof(cx<T>);
+    if (p.comp_rows || p.windowed || smem_a > 48 * 1024) return 1;
+    ParCall<T> c{p.E, p.angles, p.idx, p.ph, p.Eout, p.stream_stride, p.L, p.A, p.N};
+    return par_run<T>(c, nstream, st, [&](T *D, long long Lp) {
+        bps_par_dist_generic_kernel<T><<<dim3((unsigned)(Lp / PAR_RC), (unsigned)nstream), 256, smem_a, st>>>(p, D, Lp);
+    });
+}
+template int bps_par_generic_launch<float>(const BpsParams<float> &, int64_t, cudaStream_t);
+template int bps_par_generic_launch<double>(const BpsParams<double> &, int64_t, cudaStream_t);
 
 }  // namespace qb

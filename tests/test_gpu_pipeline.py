@@ -619,33 +619,40 @@ def test_receiver_step_is_graph_capturable_with_stage_events(env):
         assert all(s.elapsed_time(e) > 0 for _, (s, e) in events)
 
 
-@pytest.mark.parametrize("M,A,N,L", [(64, 64, 45, 70001), (16, 32, 21, 40000), (64, 96, 8, 33333), (16, 128, 33, 50000)])
-def test_bps_phase_parallel_form_on_long_streams_with_cycle_slips(env, qb_option, M, A, N, L):
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+@pytest.mark.parametrize("M,A,N,L", [(64, 64, 45, 70001), (16, 32, 21, 40000), (64, 96, 8, 33333), (16, 128, 33, 50000),
+                                     (32, 64, 20, 45000)])
+def test_bps_phase_parallel_form_on_long_streams_with_cycle_slips(env, qb_option, M, A, N, L, dtype):
     """Few long streams take the phase-parallel form (bps_par.cu: distances, running sums, arg-min, unwrap and rotation
-    as separate kernels over a scratch matrix).  A fast Wiener phase walk makes np.unwrap act many times (the serial
-    fold of phase D), a NaN and a huge sample exercise the clamp; phases, indices and rotated symbols must be
-    bit-identical to the fused mapping, with and without the caller's index array, and equal to the oracle's."""
+    as separate kernels over a scratch matrix): complex64 on a rectangular alphabet with the packed slicer, complex128
+    and cross alphabets (32-QAM: search over the alphabet) with the generic distance.  A fast Wiener phase walk makes
+    np.unwrap act many times (the serial fold of phase D), a NaN and a huge sample exercise the clamp; phases, indices
+    and rotated symbols must be bit-identical to the one-CTA-per-stream mappings, with and without the caller's index
+    array, and the indices equal to the oracle's."""
     t = env.torch
-    alphabet = env.theory.normalised_symbols(M).astype(np.complex64)
-    tables = env.device.BpsTables(A, alphabet, np.complex64, env.dev)
+    rt = np.float32 if dtype == np.complex64 else np.float64
+    it = t.int32 if dtype == np.complex64 else t.int64
+    alphabet = env.theory.normalised_symbols(M).astype(dtype)
+    tables = env.device.BpsTables(A, alphabet, dtype, env.dev)
     rng = np.random.default_rng(L)
     walk = np.cumsum(rng.standard_normal((3, L)) * 0.08, axis=1)
     x = alphabet[rng.integers(0, M, (3, L))] * np.exp(1j * walk) + 0.05 * (rng.standard_normal((3, L)) + 1j * rng.standard_normal((3, L)))
-    x = x.astype(np.complex64)
+    x = x.astype(dtype)
     x[1, 1234] = np.nan
     x[2, 4321] = 1e20
     xd = t.from_numpy(x).to(env.dev)
-    qb_option("BPS_SPLIT", "0")
+    bits = lambda v: (t.view_as_real(v) if v.is_complex() else v).contiguous().view(it)
+    qb_option("BPS_SPLIT", "0")                        # one CTA per stream (fused / tile kernels)
     out0, ph0, idx0 = env.device.bps(xd, tables, N)
     qb_option("BPS_SPLIT", None)                       # default dispatch: phase-parallel for this shape
+    l0 = env.device._lib.launch_count()
     out1, ph1, idx1 = env.device.bps(xd, tables, N)
+    assert env.device._lib.launch_count() - l0 == 5, "the five phases"
     out2, ph2, _ = env.device.bps(xd, tables, N, want_idx=False)
     assert t.equal(idx0, idx1)
-    assert t.equal(ph0.view(t.int32), ph1.view(t.int32)) and t.equal(ph1.view(t.int32), ph2.view(t.int32))
-    assert t.equal(out0.view(t.float32).view(t.int32), out1.view(t.float32).view(t.int32))
-    assert t.equal(out1.view(t.float32).view(t.int32), out2.view(t.float32).view(t.int32))
-    steps = np.abs(np.diff(ph1[0].cpu().numpy()))
+    assert t.equal(bits(ph0), bits(ph1)) and t.equal(bits(ph1), bits(ph2))
+    assert t.equal(bits(out0), bits(out1)) and t.equal(bits(out1), bits(out2))
     assert float(ph1[0].abs().max()) > np.pi / 4, "the walk must leave the search range: unwrap has acted"
-    ang = np.linspace(-np.pi / 4, np.pi / 4, A, endpoint=False, dtype=np.float32).reshape(1, -1)
+    ang = np.linspace(-np.pi / 4, np.pi / 4, A, endpoint=False, dtype=rt).reshape(1, -1)
     idr = env.co.bps_streams(x, ang, alphabet, N)
     assert np.array_equal(idx1.cpu().numpy()[:, N:L - N], idr[:, N:L - N])
