@@ -498,6 +498,26 @@ def dropin_records(dev):
         out.append({"script": name + " (equaliser + bps, host arrays in and out)", "dtype": "complex64", "symbols": nsym,
                     "ntaps": ntaps, "methods": list(methods), "bps": [A, N], "gpu_s": min(tg), "cpu_s": tc,
                     "speedup": tc / min(tg), "rms_diff": float(np.sqrt(np.mean(np.abs(rg - rc) ** 2)))})
+    # phaserec.bps alone on one capture (few long streams: the phase-parallel form, csrc/bps_par.cu)
+    for dt, nsym in ((np.complex64, 10 ** 7), (np.complex128, 10 ** 6)):
+        M, A, N = 64, 64, 45
+        al = theory.normalised_symbols(M).astype(dt)
+        rng = np.random.default_rng(7)
+        E = (al[rng.integers(0, M, (2, nsym))] * np.exp(0.1j)
+             + 0.03 * (rng.standard_normal((2, nsym)) + 1j * rng.standard_normal((2, nsym)))).astype(dt)
+        tg = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rg = ph.bps(E, A, al, N)
+            torch.cuda.synchronize()
+            tg.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        rc = co.bps_driver(E, A, al, N, kind="fast_native")
+        tc = time.perf_counter() - t0
+        out.append({"script": "phaserec.bps on one capture (host arrays in and out)", "dtype": np.dtype(dt).name,
+                    "symbols": nsym, "bps": [A, N], "gpu_s": min(tg), "cpu_s": tc, "speedup": tc / min(tg),
+                    "phase_max_diff": float(np.max(np.abs(rg[1] - rc[1])))})
     return out
 
 

@@ -24,9 +24,10 @@ def bps(E, Mtestangles, symbols, N, method="pyt", **kwargs):
     Ed = torch.from_numpy(np.ascontiguousarray(Ew)).to(dev)
     out, ph, _ = device.bps(Ed, tables, int(N), want_idx=False, accum=kwargs.get("accum", "exact"))
     ph = ph.cpu().numpy()
-    # keep the SignalObject subclass (and its attributes) of the input, like Ew*np.exp(1j*ph) does
-    Eout = np.atleast_2d(Ein).astype(E.dtype)
-    Eout[...] = out.cpu().numpy()
+    # keep the SignalObject subclass (and its attributes) of the input, like Ew*np.exp(1j*ph) does; the device result
+    # is copied straight into the new array (no intermediate host copy)
+    Eout = np.empty_like(np.atleast_2d(Ein), dtype=E.dtype, order='C')
+    torch.from_numpy(np.asarray(Eout)).copy_(out)
     if E.ndim == 1:
         return Eout.flatten(), ph.flatten()
     return Eout, ph
