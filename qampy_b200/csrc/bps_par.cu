@@ -18,9 +18,9 @@
 // Phase A's lane owns an angle and stores 8 consecutive rows as two 16-byte vectors.  Phase B's lane owns an angle and
 // walks down its column: a tile of 128 rows x 32 angles is one contiguous 16.5 kB block that comes and goes as ONE bulk
 // copy each way (cp.async.bulk + mbarrier, seven tiles on their way in, up to four out); LDS.128 -> four dependent
-// FADDs -> STS.128 in place, the memory instructions placed between the FADDs.  Measured 8.6 cycles per row (the FADD
-// chain alone is 4.4; a lone warp's issue cadence with the 128-bit shared-memory accesses makes up the rest; without
-// the store 7.6).  What was tried on the way: a plain column-major matrix, 40 MB from one angle to the next at 1e7
+// FADDs -> STS.128 in place, the memory instructions placed between the FADDs.  Measured 8.4 cycles per row = 1077 per
+// tile (clock64 in the kernel): 683 in the adds (5.3 per row against the 4.4 of the bare FADD chain), 205 in lane 0's
+// wait_group / expect_tx / bulk load and the mbarrier wait, 124 in the proxy fence and the bulk store.  What was tried on the way: a plain column-major matrix, 40 MB from one angle to the next at 1e7
 // rows: 33 cycles per row in TLB misses; 512-byte bulk copies per column: 34 cycles per row.  Phase C's thread owns a
 // ROW and walks over the angles (coalesced along rows, strict < in ascending angle order = the reference's first
 // minimum).  Phase D evaluates a batch of 512 rows at once and enters the serial fold of np.unwrap's corrections only
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(32) bps_par_csum_kernel(T *D, long long Lp, lo
         T *stage = tiles + (size_t)(t % G::ST) * 32 * G::TRP;
         if constexpr (sizeof(T) == 4) {
             const uint32_t my = smem_u32(stage + lane * G::TRP);
-            // Software pipeline in groups of 4 rows: the LDS.128 of group g + 2 and the STS.128 of group g - 1 sit
+            // Software pipeline in groups of 4 rows: the LDS.128 of group g + 4 and the STS.128 of group g - 1 sit
             // between the four dependent FADDs of group g (volatile, so that they stay where they are written)
             auto lds = [&](int g) {
                 float4 v;
@@ -251,25 +251,25 @@ __global__ void __launch_bounds__(32) bps_par_csum_kernel(T *D, long long Lp, lo
             auto sts = [&](int g, const float4 &v) {
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my + 16u * g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
             };
-            constexpr int NG = PAR_TR / 4;
-            float4 v0 = lds(0), v1 = lds(1), done = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t == 0) v0.x = 0.f;                                        // row 0 is never added (pythran_dsp.py:30)
+            constexpr int NG = PAR_TR / 4, PF = 4;                         // groups per tile, groups loaded ahead
+            float4 q[PF], done = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int g = 0; g < PF; g++) q[g] = lds(g);
+            if (t == 0) q[0].x = 0.f;                                      // row 0 is never added (pythran_dsp.py:30)
 #pragma unroll
             for (int g = 0; g < NG; g++) {
-                float4 v2 = make_float4(0.f, 0.f, 0.f, 0.f);
-                csum = __fadd_rn(csum, v0.x);                              // :33/:36, sequential
-                v0.x = csum;
-                if (g + 2 < NG) v2 = lds(g + 2);
-                csum = __fadd_rn(csum, v0.y);
-                v0.y = csum;
+                float4 v = q[g % PF];
+                csum = __fadd_rn(csum, v.x);                               // :33/:36, sequential
+                v.x = csum;
+                if (g + PF < NG) q[g % PF] = lds(g + PF);
+                csum = __fadd_rn(csum, v.y);
+                v.y = csum;
                 if (g > 0) sts(g - 1, done);
-                csum = __fadd_rn(csum, v0.z);
-                v0.z = csum;
-                csum = __fadd_rn(csum, v0.w);
-                v0.w = csum;
-                done = v0;
-                v0 = v1;
-                v1 = v2;
+                csum = __fadd_rn(csum, v.z);
+                v.z = csum;
+                csum = __fadd_rn(csum, v.w);
+                v.w = csum;
+                done = v;
             }
             sts(NG - 1, done);
         } else {
