@@ -77,6 +77,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays of the step")
     ap.add_argument("--no-dropin", action="store_true", help="skip the single-capture drop-in records (script shapes)")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record (one 1e9-sample capture over the ranks)")
+    ap.add_argument("--no-pin", action="store_true", help="e2e path: leave the process on whatever CPUs it was given "
+                                                          "instead of binding it to the CPUs next to its GPU")
     ap.add_argument("--no-taper", action="store_true", help="e2e path: do not cut the last chunk into 1/2 + 1/4 + 1/4")
     return ap.parse_args()
 
@@ -105,6 +107,27 @@ def workload_config(a, world):
 # ------------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------
+def pin_to_gpu_cpus(sampler):
+    """Run this process on the CPUs next to its GPU (NVML's CPU affinity of the device) so that the pinned host buffers
+    of the e2e path are allocated on the GPU's NUMA node: a capture that crosses the socket link moves at 77 instead of
+    98 GB/s (both directions, one GPU).  Returns (previous affinity, CPUs chosen) or (None, None)."""
+    try:
+        nvml, handle = sampler.nvml, sampler.handle
+        if nvml is None or handle is None or not hasattr(os, "sched_setaffinity"):
+            return None, None
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = nvml.nvmlDeviceGetCpuAffinity(handle, words)
+        near = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus = sorted(near & before)
+        if not cpus or set(cpus) == set(before):
+            return None, None
+        os.sched_setaffinity(0, cpus)
+        return before, cpus
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  The region lasts tens of milliseconds, so
     the sampler polls NVML in a thread (every 2 ms) instead of `nvidia-smi -lms`, whose first line arrives
@@ -736,6 +759,7 @@ def run_b200(a, rank, local_rank, world):
     # of both stages (what the reference call returns), with the copies of neighbouring chunks overlapping the
     # compute (pipeline.run_host)
     e2e = None
+    affinity_before, near_cpus = (None, None) if (a.no_e2e or a.no_pin) else pin_to_gpu_cpus(sampler)
     if not a.no_e2e:
         E = caps[0][0]
         Eh = torch.empty(E.shape, dtype=E.dtype, pin_memory=True)
@@ -796,6 +820,11 @@ def run_b200(a, rank, local_rank, world):
                                 / (link_gbs * 1e9) * 1e3,
                                 "note": "all ranks copying pinned memory H2D and D2H at once (256 MB each way, slowest "
                                         "rank): what the host side of this box moves, the ceiling of any e2e number"}
+            if near_cpus:
+                e2e["cpu_affinity"] = "process bound to the %d CPUs NVML lists next to its GPU (%d-%d) while the pinned " \
+                                      "buffers are allocated and used" % (len(near_cpus), near_cpus[0], near_cpus[-1])
+    if affinity_before is not None:
+        os.sched_setaffinity(0, affinity_before)      # the CPU baseline below uses every core it is allowed
     c5 = None
     if a.workload == "c3" and not a.no_c5:
         caps.clear()
