@@ -450,7 +450,6 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
     while (RR < BPS_TR + W) RR <<= 1;
     const size_t smem = ((size_t)RR * A + (size_t)A * (BPS_TR + 1) + A) * sizeof(T) +
                         (A + BPS_TR + (n_re ? n_re + n_im : M)) * sizeof(cx<T>) + 64;
-    if (smem > 200 * 1024) return set_error(QB_ERR_UNSUPPORTED, "bps: 2N*A too large for the shared-memory ring");
     p.tile_rows = BPS_TR;
     p.ring_rows = RR;
     // set on every launch: the attribute belongs to the device that is current, and it is cheap
@@ -489,6 +488,16 @@ static int launch_bps(const void *E, int64_t nstream, int64_t stream_stride, int
             return QB_OK;
         }
     }
+    if (smem > 200 * 1024) {
+        // the ring of 2N rows does not fit: the phase-parallel form keeps its history in HBM and has no such limit
+        if (A <= 128) {
+            const int rc = bps_par_generic_launch<T>(p, nstream, st);
+            if (rc <= 0) return rc;
+        }
+        return set_error(QB_ERR_UNSUPPORTED, "bps: 2N*A too large for the shared-memory ring");
+    }
+    p.tile_rows = BPS_TR;
+    p.ring_rows = RR;
     bps_kernel<T><<<(unsigned)nstream, BPS_THREADS, smem, st>>>(p);
     count_launch();
     QB_CUDA_CHECK(cudaGetLastError());

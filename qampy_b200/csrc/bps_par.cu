@@ -27,7 +27,9 @@
 // for a batch that has one (2.7 cycles per row).  1 kB of HBM traffic per row, which is why this form is for few
 // streams only: many streams keep the fused kernel, whose distances never leave the lane.
 //
-// complex128 signals and alphabets without a rectangular grid take the same phases with the distance of bps.cu (generic
+// Any number of test angles up to 128 (the matrix has whole blocks of 32 columns; the padding columns are never
+// read), and no limit on 2N x A: the history lives in HBM, not in a shared-memory ring -- shapes the tile kernels of
+// bps.cu reject (complex128, 100 angles, N = 70) run here.  complex128 signals and alphabets without a rectangular grid take the same phases with the distance of bps.cu (generic
 // slicer / search over the alphabet) in phase A and double-precision sums (DADD chain: 8.8 cycles per row).
 //
 // One capture of two polarisations, 64 angles (scratch/bps_par_time.py): 1e7 rows 63 ms against 408 ms in the producer /
@@ -79,6 +81,7 @@ struct ParCall {
     cx<T> *Eout;
     long long stream_stride, L;
     int A, N;
+    int Ap;            // A rounded up to whole blocks of 32 angles: the matrix's column count (columns >= A are never read)
 };
 
 // ---- A (complex64, rectangular alphabet): distances with the packed slicer of bps_fast.cu -----------------------------
@@ -160,8 +163,9 @@ __global__ void __launch_bounds__(256) bps_par_dist_generic_kernel(BpsParams<T> 
     }
     __syncthreads();
     const cx<T> *E = p.E + (long long)blockIdx.y * p.stream_stride;
-    T *mat = D + (long long)blockIdx.y * par_stream_elems<T>(A, Lp);
-    const int nw = A / 32;
+    const int Ap = (A + 31) / 32 * 32;
+    T *mat = D + (long long)blockIdx.y * par_stream_elems<T>(Ap, Lp);
+    const int nw = Ap / 32;
     const long long last = p.L - 1;
     // units of work: (group of 8 rows, block of 32 angles); lane = angle
     for (int u = warp; u < nw * (PAR_RC / PAR_NR); u += 8) {
@@ -169,11 +173,12 @@ __global__ void __launch_bounds__(256) bps_par_dist_generic_kernel(BpsParams<T> 
         const long long i = (long long)blockIdx.x * PAR_RC + (long long)g * PAR_NR;
         if (i >= p.L) break;
         const int a = cb * 32 + lane;
+        if (a >= A) continue;                              // padding columns of the last block: never read
         const cx<T> c = comp[a];
         T d[PAR_NR];
 #pragma unroll
         for (int k = 0; k < PAR_NR; k++) d[k] = min_distance<T>(E[min(i + k, last)], c, slicer, pre, pim, gre, gim, syms, p.M);
-        T *dst = mat + par_at<T>(A, a, i);
+        T *dst = mat + par_at<T>(Ap, a, i);
         if constexpr (sizeof(T) == 4) {
             reinterpret_cast<float4 *>(dst)[0] = make_float4(d[0], d[1], d[2], d[3]);
             reinterpret_cast<float4 *>(dst)[1] = make_float4(d[4], d[5], d[6], d[7]);
@@ -298,15 +303,15 @@ __global__ void __launch_bounds__(32) bps_par_csum_kernel(T *D, long long Lp, lo
 
 // ---- C: window differences and their first arg-min; thread = output row ----------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) bps_par_argmin_kernel(const T *C, long long Lp, long long L, int A, int N,
+__global__ void __launch_bounds__(256) bps_par_argmin_kernel(const T *C, long long Lp, long long L, int A, int Ap, int N,
                                                              int32_t *idx)
 {
     const long long lo = N < L ? N : L;
     const long long hi = (L - N > lo) ? L - N : lo;
     const long long j = lo + (long long)blockIdx.x * 256 + threadIdx.x;
     if (j >= hi) return;
-    const T *cs = C + (long long)blockIdx.y * par_stream_elems<T>(A, Lp);
-    const T *up = cs + par_at<T>(A, 0, j + N), *dn = cs + par_at<T>(A, 0, j - N);   // csum[i], csum[i - 2N], i = j + N
+    const T *cs = C + (long long)blockIdx.y * par_stream_elems<T>(Ap, Lp);
+    const T *up = cs + par_at<T>(Ap, 0, j + N), *dn = cs + par_at<T>(Ap, 0, j - N);   // csum[i], csum[i - 2N], i = j + N
     T best = (T)1000.;                                       // dmin0 = 1000 (:31): nothing below it -> idx stays 0
     int bk = 0;
 #pragma unroll 8
@@ -443,7 +448,8 @@ static long long par_padded_rows(long long L) { return (L + PAR_RC - 1) / PAR_RC
 size_t bps_par_scratch_bytes(int64_t nstream, int64_t L, int64_t A, bool own_idx, int elem)
 {
     const long long Lp = par_padded_rows(L);
-    const size_t mat = elem == 4 ? (size_t)par_stream_elems<float>((int)A, Lp) * 4 : (size_t)par_stream_elems<double>((int)A, Lp) * 8;
+    const int Ap = (int)((A + 31) / 32 * 32);
+    const size_t mat = elem == 4 ? (size_t)par_stream_elems<float>(Ap, Lp) * 4 : (size_t)par_stream_elems<double>(Ap, Lp) * 8;
     return (size_t)nstream * mat + (own_idx ? (size_t)nstream * L * sizeof(int32_t) : 0);
 }
 
@@ -453,7 +459,7 @@ static int par_run(const ParCall<T> &c, int64_t nstream, cudaStream_t st, Launch
 {
     using G = ParGeom<T>;
     const long long L = c.L, Lp = par_padded_rows(L);
-    const size_t mat = (size_t)nstream * par_stream_elems<T>(c.A, Lp) * sizeof(T);
+    const size_t mat = (size_t)nstream * par_stream_elems<T>(c.Ap, Lp) * sizeof(T);
     T *D = nullptr;
     int32_t *own_idx = nullptr;
     {
@@ -487,9 +493,9 @@ static int par_run(const ParCall<T> &c, int64_t nstream, cudaStream_t st, Launch
                 rc = set_error(QB_ERR_CUDA, "bps: cudaFuncSetAttribute failed");
                 break;
             }
-            bps_par_csum_kernel<T><<<(unsigned)(nstream * (c.A / 32)), 32, smem_b, st>>>(D, Lp, L, c.A);
+            bps_par_csum_kernel<T><<<(unsigned)(nstream * (c.Ap / 32)), 32, smem_b, st>>>(D, Lp, L, c.Ap);
             count_launch();
-            bps_par_argmin_kernel<T><<<dim3((unsigned)((hi - lo + 255) / 256), (unsigned)nstream), 256, 0, st>>>(D, Lp, L, c.A, c.N, idx);
+            bps_par_argmin_kernel<T><<<dim3((unsigned)((hi - lo + 255) / 256), (unsigned)nstream), 256, 0, st>>>(D, Lp, L, c.A, c.Ap, c.N, idx);
             count_launch();
             if (c.ph) {
                 bps_par_unwrap_kernel<T><<<(unsigned)nstream, 32, 0, st>>>(idx, c.angles, c.A, L, c.N, c.ph);
@@ -512,8 +518,8 @@ static int par_run(const ParCall<T> &c, int64_t nstream, cudaStream_t st, Launch
 // BPS_SPLIT = 2 (qb_set_option) forces it, 0 / 1 exclude it (tests run all mappings).
 bool bps_par_wanted(int64_t nstream, int64_t L, int64_t A, bool own_idx, int elem)
 {
-    if (A % 32 != 0 || A > 128 || nstream < 1) return false;
-    bool par = L >= 32768 && nstream * (A / 32) <= 64;
+    if (A < 1 || A > 128 || nstream < 1) return false;
+    bool par = L >= 32768 && nstream * ((A + 31) / 32) <= 64;
     if (const char e = option_char(OPT_BPS_SPLIT)) par = e == '2' && L >= 1;
     if (par) {
         size_t free_b = 0, total_b = 0;
@@ -526,7 +532,7 @@ bool bps_par_wanted(int64_t nstream, int64_t L, int64_t A, bool own_idx, int ele
 template <int NW>
 static int launch_par_fast(const BpsFastParams &p, int64_t nstream, cudaStream_t st)
 {
-    ParCall<float> c{p.E, p.angles, p.idx, p.ph, p.Eout, p.stream_stride, p.L, p.A, p.N};
+    ParCall<float> c{p.E, p.angles, p.idx, p.ph, p.Eout, p.stream_stride, p.L, p.A, p.N, p.A};   // A % 32 == 0 here
     return par_run<float>(c, nstream, st, [&](float *D, long long Lp) {
         bps_par_dist_kernel<NW><<<dim3((unsigned)(Lp / PAR_RC), (unsigned)nstream), 64 * NW, par_dist_smem(NW, p.n_re, p.n_im), st>>>(p, D, Lp);
     });
@@ -550,7 +556,7 @@ int bps_par_generic_launch(const BpsParams<T> &p, int64_t nstream, cudaStream_t 
     const bool slicer = p.n_re > 0;
     const size_t smem_a = (size_t)(p.A + (slicer ? p.n_re + p.n_im : p.M)) * sizeof(cx<T>);
     if (p.comp_rows || p.windowed || smem_a > 48 * 1024) return 1;
-    ParCall<T> c{p.E, p.angles, p.idx, p.ph, p.Eout, p.stream_stride, p.L, p.A, p.N};
+    ParCall<T> c{p.E, p.angles, p.idx, p.ph, p.Eout, p.stream_stride, p.L, p.A, p.N, (p.A + 31) / 32 * 32};
     return par_run<T>(c, nstream, st, [&](T *D, long long Lp) {
         bps_par_dist_generic_kernel<T><<<dim3((unsigned)(Lp / PAR_RC), (unsigned)nstream), 256, smem_a, st>>>(p, D, Lp);
     });

@@ -621,7 +621,7 @@ def test_receiver_step_is_graph_capturable_with_stage_events(env):
 
 @pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
 @pytest.mark.parametrize("M,A,N,L", [(64, 64, 45, 70001), (16, 32, 21, 40000), (64, 96, 8, 33333), (16, 128, 33, 50000),
-                                     (32, 64, 20, 45000)])
+                                     (32, 64, 20, 45000), (16, 100, 70, 36000), (64, 28, 14, 52000)])
 def test_bps_phase_parallel_form_on_long_streams_with_cycle_slips(env, qb_option, M, A, N, L, dtype):
     """Few long streams take the phase-parallel form (bps_par.cu: distances, running sums, arg-min, unwrap and rotation
     as separate kernels over a scratch matrix): complex64 on a rectangular alphabet with the packed slicer, complex128
@@ -643,15 +643,20 @@ def test_bps_phase_parallel_form_on_long_streams_with_cycle_slips(env, qb_option
     xd = t.from_numpy(x).to(env.dev)
     bits = lambda v: (t.view_as_real(v) if v.is_complex() else v).contiguous().view(it)
     qb_option("BPS_SPLIT", "0")                        # one CTA per stream (fused / tile kernels)
-    out0, ph0, idx0 = env.device.bps(xd, tables, N)
+    try:
+        out0, ph0, idx0 = env.device.bps(xd, tables, N)
+    except NotImplementedError:                        # 2N x A doubles do not fit the tile kernels' shared-memory ring;
+        assert dtype == np.complex128 and 2 * N * A >= 14000   # the phase-parallel form has no such limit
+        out0 = None
     qb_option("BPS_SPLIT", None)                       # default dispatch: phase-parallel for this shape
     l0 = env.device._lib.launch_count()
     out1, ph1, idx1 = env.device.bps(xd, tables, N)
     assert env.device._lib.launch_count() - l0 == 5, "the five phases"
     out2, ph2, _ = env.device.bps(xd, tables, N, want_idx=False)
-    assert t.equal(idx0, idx1)
-    assert t.equal(bits(ph0), bits(ph1)) and t.equal(bits(ph1), bits(ph2))
-    assert t.equal(bits(out0), bits(out1)) and t.equal(bits(out1), bits(out2))
+    if out0 is not None:
+        assert t.equal(idx0, idx1)
+        assert t.equal(bits(ph0), bits(ph1)) and t.equal(bits(out0), bits(out1))
+    assert t.equal(bits(ph1), bits(ph2)) and t.equal(bits(out1), bits(out2))
     assert float(ph1[0].abs().max()) > np.pi / 4, "the walk must leave the search range: unwrap has acted"
     ang = np.linspace(-np.pi / 4, np.pi / 4, A, endpoint=False, dtype=rt).reshape(1, -1)
     idr = env.co.bps_streams(x, ang, alphabet, N)
