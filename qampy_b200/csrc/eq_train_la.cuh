@@ -106,7 +106,7 @@ __device__ __forceinline__ void tile_gram(const float *tile, int nslots, int nmo
     }
 }
 
-// GRID (sbd / dd only): the decision of a searched alphabet is compiled in -- 1 grid slicer, 0 list search -- so that
+// GRID (sbd / dd / mddma only): the decision of a searched alphabet is compiled in -- 1 grid slicer, 0 list search -- so that
 // no branch sits in the symbol loop.  Whether an alphabet is a grid is found out in the kernel (detect_grid), so
 // both instantiations are launched back to back and each one works on the streams whose alphabet is its kind (all
 // or none of them in practice; the other launch returns after its prologue).  -1: decided at run time.
@@ -491,7 +491,7 @@ static int launch_la_one(const TrainParams<float> &p, const FastGeom &g, size_t 
 template <int LPS, int NQ, int METHOD, int NMASK, bool ADAPT>
 static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem, cudaStream_t st)
 {
-    if constexpr (METHOD == QB_SBD || METHOD == QB_DD) {
+    if constexpr (METHOD == QB_SBD || METHOD == QB_DD || METHOD == QB_MDDMA) {
         if (p.nsym_pitch > p.nsym_smem) {    // grid scratch staged: one launch per decision kind (see the kernel)
             const int rc = launch_la_one<LPS, NQ, METHOD, NMASK, 1, ADAPT>(p, g, smem, st);
             if (rc != QB_OK) return rc;
@@ -527,6 +527,8 @@ static int launch_la_method(const TrainParams<float> &p, const FastGeom &g, size
         return launch_la_pad<LPS, NQ, QB_SBD, ADAPT>(p, g, smem, st);
     case QB_DD:
         return launch_la_pad<LPS, NQ, QB_DD, ADAPT>(p, g, smem, st);
+    case QB_MDDMA:
+        return launch_la_pad<LPS, NQ, QB_MDDMA, ADAPT>(p, g, smem, st);
     case QB_RDE:
         if ((p.K + 1) / 2 > MAXC) return launch_la_pad<LPS, NQ, METHOD_GENERIC, ADAPT>(p, g, smem, st);
         if (p.K - (p.K + 1) / 2 <= 3) return launch_la_pad<LPS, NQ, METHOD_RDE3, ADAPT>(p, g, smem, st);
