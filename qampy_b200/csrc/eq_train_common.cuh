@@ -6,6 +6,13 @@
 namespace qb {
 
 constexpr int GRID_MAX_K = 256;   // largest alphabet the grid slicer of the fast kernels handles (one byte per point)
+// levels per axis of the smallest square grid that holds K points (cross QAM: 32 -> 6, 128 -> 12)
+__host__ __device__ __forceinline__ int grid_side(int K)
+{
+    int n = 2;
+    while (n * n < K) n++;
+    return n;
+}
 
 template <typename T>
 struct TrainParams {

@@ -35,7 +35,8 @@ int train_fast_try(TrainParams<float> p, cudaStream_t st)
     // methods that search their alphabet get scratch for the grid slicer behind the staged constants
     // (eq_train_fast.cuh, detect_grid): 32 axis levels + one byte per alphabet point
     const bool searched = p.method == QB_SBD || p.method == QB_DD || p.method == QB_MDDMA;
-    p.nsym_pitch = p.nsym_smem + ((searched && p.K >= 4 && p.K <= GRID_MAX_K) ? 16 + (p.K + 7) / 8 : 0);
+    const int side = grid_side(p.K);     // levels per axis of the smallest square grid that holds K points
+    p.nsym_pitch = p.nsym_smem + ((searched && p.K >= 4 && p.K <= GRID_MAX_K && side <= 16) ? 16 + (side * side + 7) / 8 : 0);
     // option TRAIN_LPS = 8 | 16 (qb_set_option) forces a layout (tests, tuning)
     const int forced = option_int(OPT_TRAIN_LPS, 0);
     // Default: 8 lanes per stream (fewest instructions per trained symbol; measured fastest from 2 to

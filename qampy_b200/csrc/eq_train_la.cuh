@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
         detect_grid<LPS>(ec, mysyms, p.nsym_smem, reinterpret_cast<float *>(mysyms + p.nsym_smem), gl);
     bool act = active;              // this launch records results for this lane's stream
     if (GRID >= 0) {
-        const bool mine = (ec.gn != 0) == (GRID == 1);
+        const int kind = ec.gn == 0 ? 0 : (ec.gholes ? 2 : 1);     // list search, full grid, grid with empty cells
+        const bool mine = kind == GRID;
         if (!__any_sync(0xffffffffu, mine && active)) return;
         act = active && mine;
     }
@@ -493,7 +494,9 @@ static int launch_la(const TrainParams<float> &p, const FastGeom &g, size_t smem
 {
     if constexpr (METHOD == QB_SBD || METHOD == QB_DD || METHOD == QB_MDDMA) {
         if (p.nsym_pitch > p.nsym_smem) {    // grid scratch staged: one launch per decision kind (see the kernel)
-            const int rc = launch_la_one<LPS, NQ, METHOD, NMASK, 1, ADAPT>(p, g, smem, st);
+            const int side = grid_side(p.K);
+            const int rc = side * side == p.K ? launch_la_one<LPS, NQ, METHOD, NMASK, 1, ADAPT>(p, g, smem, st)
+                                              : launch_la_one<LPS, NQ, METHOD, NMASK, 2, ADAPT>(p, g, smem, st);
             if (rc != QB_OK) return rc;
         }
         return launch_la_one<LPS, NQ, METHOD, NMASK, 0, ADAPT>(p, g, smem, st);
