@@ -149,8 +149,11 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     // and flushed at the end of the tile: they share one region, which keeps a warp's slice small enough for
     // 8 warps per SM when a launch holds more than one wave of streams (long captures).
     float2 *gsum = gbuf + g.nslots * g.tile_syms;
-    float2 *errs = gsum;                                    // [GPW][tile_syms]
-    const int shared_len = max(g.nslots * gram_sum_len(g.tile_syms, p.ntaps), GPW * g.tile_syms);
+    // [GPW][tile_syms + 1]: the lane groups of a warp store the errors of their streams with ONE instruction, so the
+    // rows sit one float2 apart in the banks (a pitch of tile_syms put all groups on one bank pair: 10 M of the 15 M
+    // excessive shared-memory wavefronts of a C3 training launch)
+    float2 *errs = gsum;
+    const int shared_len = max(g.nslots * gram_sum_len(g.tile_syms, p.ntaps), GPW * (g.tile_syms + 1));
     float2 *syms = gsum + shared_len;                       // [GPW][nsym_smem]
 
     const float2 *gsyms = p.symbols + (long long)mode * p.K;
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
     }
     float mu = p.mu[stream];
     float2 eprev = make_float2(0.f, 0.f);    // ADAPT: error of the symbol before
-    const uint32_t errs_addr = smem_u32(errs + grp * g.tile_syms);
+    const uint32_t errs_addr = smem_u32(errs + grp * (g.tile_syms + 1));
     __syncwarp();
     ErrConst ec = load_err_const<METHOD>(mysyms, p.nsym_smem);
     if (p.nsym_pitch > p.nsym_smem)   // searched alphabet: is it a square grid? (uniform)
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(32 * TRAIN_WPB) train_la_kernel(TrainParams<fl
         __syncwarp();
         if (p.err && act) {
             float2 *eg = p.err + ((long long)seg * p.nmodes + mode) * (p.TrSyms * p.Niter) + it * p.TrSyms + i0;
-            for (int c = gl; c < n; c += LPS) eg[c] = errs[grp * g.tile_syms + c];
+            for (int c = gl; c < n; c += LPS) eg[c] = errs[grp * (g.tile_syms + 1) + c];
         }
         __syncwarp();
     }
@@ -463,7 +466,7 @@ static int la_geometry(const TrainParams<float> &p, FastGeom &g, size_t &smem)
     g.nslots = (GPW % p.nsel == 0) ? GPW / p.nsel : (GPW / p.nsel + 2 < GPW ? GPW / p.nsel + 2 : GPW);
     if (g.nslots < 1) g.nslots = 1;
     if (2 * g.tile_syms + g.lpp * nq + 2 > 32 * GRAM_CH) return 0;
-    const size_t shared_len = std::max((size_t)g.nslots * gram_sum_len(g.tile_syms, p.ntaps), (size_t)GPW * g.tile_syms);
+    const size_t shared_len = std::max((size_t)g.nslots * gram_sum_len(g.tile_syms, p.ntaps), (size_t)GPW * (g.tile_syms + 1));
     smem = ((size_t)2 * g.nslots * p.nmodes * g.pitch + (size_t)g.nslots * g.tile_syms + shared_len +
             (size_t)GPW * p.nsym_pitch) * sizeof(float2);
     if (smem > 56 * 1024) return 0;   // four warp slices per CTA must fit 227 kB
