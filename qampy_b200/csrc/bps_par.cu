@@ -13,24 +13,25 @@
 //                                                                                     per step
 //   E  rotation of the input by the phase, edges (phaserecovery.py:155-159)        -- independent
 //
-// The matrix lives in HBM in TILES of 128 rows: D[stream][tile][angle][128 rows + 16 bytes of padding] (one float, or one
-// double for complex128 signals, per entry).
-// Phase A's lane owns an angle and stores 8 consecutive rows as two 16-byte vectors.  Phase B's lane owns an angle and
-// walks down its column: a tile of 128 rows x 32 angles is one contiguous 16.5 kB block that comes and goes as ONE bulk
-// copy each way (cp.async.bulk + mbarrier, seven tiles on their way in, up to four out); LDS.128 -> four dependent
-// FADDs -> STS.128 in place, the memory instructions placed between the FADDs.  Measured 8.4 cycles per row = 1077 per
-// tile (clock64 in the kernel): 683 in the adds (5.3 per row against the 4.4 of the bare FADD chain), 205 in lane 0's
-// wait_group / expect_tx / bulk load and the mbarrier wait, 124 in the proxy fence and the bulk store.  What was tried on the way: a plain column-major matrix, 40 MB from one angle to the next at 1e7
-// rows: 33 cycles per row in TLB misses; 512-byte bulk copies per column: 34 cycles per row.  Phase C's thread owns a
-// ROW and walks over the angles (coalesced along rows, strict < in ascending angle order = the reference's first
-// minimum).  Phase D evaluates a batch of 512 rows at once and enters the serial fold of np.unwrap's corrections only
-// for a batch that has one (2.7 cycles per row).  1 kB of HBM traffic per row, which is why this form is for few
-// streams only: many streams keep the fused kernel, whose distances never leave the lane.
+// The matrix lives in HBM in TILES of 128 rows: D[stream][tile][angle][128 rows + 16 bytes of padding] (one float, or
+// one double for complex128 signals, per entry).  Phase A's lane owns an angle and stores 8 consecutive rows as 16-byte
+// vectors.  Phase B's lane owns an angle and walks down its column: a tile of 128 rows x 32 angles is one contiguous
+// 16.5 kB block that comes and goes as ONE bulk copy each way (cp.async.bulk + mbarrier, seven tiles on their way in,
+// up to four out); LDS.128 -> four dependent FADDs -> STS.128 in place, the memory instructions placed between the
+// FADDs.  Measured 8.4 cycles per row = 1077 per tile (clock64 in the kernel): 683 in the adds (5.3 per row against the
+// 4.4 of the bare FADD chain), 205 in lane 0's wait_group / expect_tx / bulk load and the mbarrier wait, 124 in the
+// proxy fence and the bulk store.  Tried on the way: a plain column-major matrix (40 MB from one angle to the next at
+// 1e7 rows: 33 cycles per row in TLB misses), 512-byte bulk copies per column (34 cycles per row).  Phase C's thread
+// owns a ROW and walks over the angles (coalesced along rows, strict < in ascending angle order = the reference's first
+// minimum; 5 TB/s of HBM reads).  Phase D evaluates a batch of 512 rows at once and enters the serial fold of
+// np.unwrap's corrections only for a batch that has one (2.7 cycles per row).  1 kB of HBM traffic per row, which is
+// why this form is for few streams only: many streams keep the fused kernel, whose distances never leave the lane.
 //
-// Any number of test angles up to 128 (the matrix has whole blocks of 32 columns; the padding columns are never
-// read), and no limit on 2N x A: the history lives in HBM, not in a shared-memory ring -- shapes the tile kernels of
-// bps.cu reject (complex128, 100 angles, N = 70) run here.  complex128 signals and alphabets without a rectangular grid take the same phases with the distance of bps.cu (generic
-// slicer / search over the alphabet) in phase A and double-precision sums (DADD chain: 8.8 cycles per row).
+// Any number of test angles up to 128 (the matrix has whole blocks of 32 columns; the padding columns are never read),
+// and no limit on 2N x A: the history lives in HBM, not in a shared-memory ring -- shapes the tile kernels of bps.cu
+// reject (complex128, 100 angles, N = 70) run here.  complex128 signals and alphabets without a rectangular grid take
+// the same phases with the distance of bps.cu (generic slicer / search over the alphabet) in phase A and double-
+// precision sums (DADD chain: 8.8 cycles per row).
 //
 // One capture of two polarisations, 64 angles (scratch/bps_par_time.py): 1e7 rows 63 ms against 408 ms in the producer /
 // chain mapping (12.4 against 80 cycles per row), 1e6 rows 6.5 against 40 ms, 2^17 rows 1.2 against 5.3 ms; indices and
